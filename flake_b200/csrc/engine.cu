@@ -1,0 +1,264 @@
+/*
+ * engine.cu -- host side of the CUDA engine: scratch management and the launch
+ * sequence of one chunk.  Exposes the plain C ABI of engine.h.
+ *
+ * Launch sequence per chunk (all on one stream, no host synchronisation):
+ *   k_frames_fixed | (k_vbs_split + k_frames_vbs)   frame table
+ *   k_prep      per frame      ingest, stereo decision, wasted bits, constant test
+ *   k_lpc       per subframe   FP64 window/autocorrelation/Levinson/quantise
+ *   k_search    per subframe   order + Rice search, final residual
+ *   k_pack      per frame      bit packing, CRC-8/16, verbatim size check
+ *   k_offsets   1 CTA          exclusive scan of frame lengths, chunk summary
+ *   k_compact   per frame      staged slots -> contiguous output
+ */
+#include "cuda_compat.h"
+#include "engine.h"
+#include "dev_common.cuh"
+#include "k_prep.cuh"
+#include "k_lpc.cuh"
+#include "k_search.cuh"
+#include "k_pack.cuh"
+
+#include <new>
+
+#define FB_SMEM_BUDGET (200 * 1024)
+
+struct FbEngine {
+    FbConfig cfg;
+    int device;
+    uint32_t max_blocks, max_frames, max_subs;
+    uint64_t max_samples;
+    uint64_t slot_bytes, out_bytes;
+    cudaStream_t stream;
+    /* scratch */
+    FbFrame *d_frames;
+    uint32_t *d_nframes, *d_verbatim;
+    FbSub *d_subs;
+    uint8_t *d_modes;
+    int32_t *d_smp, *d_res, *d_coefs, *d_shifts;
+    double *d_win;
+    uint8_t *d_slots;
+    uint32_t *d_frame_len;
+    uint64_t *d_frame_off;
+    uint32_t *d_vbs_sizes, *d_vbs_counts;
+    int lpc_smem_doubles, search_smem_ints, pack_smem_words;
+    uint64_t launches;
+    char err[256];
+};
+
+static void set_err(char *dst, size_t n, const char *msg, cudaError_t ce)
+{
+    if (!dst || !n) return;
+    if (ce != cudaSuccess) snprintf(dst, n, "%s: %s", msg, cudaGetErrorString(ce));
+    else snprintf(dst, n, "%s", msg);
+}
+
+#define FB_TRY_ALLOC(ptr, bytes)                                                   \
+    do {                                                                           \
+        cudaError_t ce_ = cudaMalloc((void **)&(ptr), (bytes));                    \
+        if (ce_ != cudaSuccess) { set_err(err, errlen, "cudaMalloc failed", ce_);  \
+                                  fb_engine_destroy(e); return nullptr; }          \
+    } while (0)
+
+extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t max_blocks,
+                                      char *err, size_t errlen)
+{
+    if (!cfg || max_blocks == 0) { set_err(err, errlen, "bad arguments", cudaSuccess); return nullptr; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev < 1) {
+        set_err(err, errlen, "no CUDA device (flake_b200 has no CPU fallback)", ce);
+        return nullptr;
+    }
+    if (device >= 0) {
+        ce = cudaSetDevice(device);
+        if (ce != cudaSuccess) { set_err(err, errlen, "cudaSetDevice failed", ce); return nullptr; }
+    } else {
+        cudaGetDevice(&device);
+    }
+    FbEngine *e = new (std::nothrow) FbEngine();
+    if (!e) { set_err(err, errlen, "out of host memory", cudaSuccess); return nullptr; }
+    memset(e, 0, sizeof *e);
+    e->cfg = *cfg;
+    e->device = device;
+    const int C = cfg->channels, B = cfg->block_size;
+    e->max_blocks = max_blocks;
+    e->max_frames = cfg->variable_block_size ? max_blocks * 8u : max_blocks;
+    e->max_subs = e->max_frames * (uint32_t)C;
+    e->max_samples = (uint64_t)max_blocks * (uint64_t)B;
+    if (e->max_samples * (uint64_t)(C * cfg->bps + 1) / 8u + (uint64_t)e->max_frames * 96u > 0xfff00000ull) {
+        set_err(err, errlen, "chunk too large for 32-bit slot offsets", cudaSuccess);
+        delete e; return nullptr;
+    }
+    e->slot_bytes = (uint64_t)fb_slot_offset(e->max_frames, (uint32_t)e->max_samples, C, cfg->bps) + 256u;
+    e->out_bytes = e->slot_bytes;
+
+    ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { set_err(err, errlen, "cudaStreamCreate failed", ce); delete e; return nullptr; }
+
+    const uint64_t nint = e->max_samples * (uint64_t)C;
+    FB_TRY_ALLOC(e->d_frames, sizeof(FbFrame) * (size_t)e->max_frames);
+    FB_TRY_ALLOC(e->d_nframes, sizeof(uint32_t) * 4);
+    e->d_verbatim = e->d_nframes + 1;
+    FB_TRY_ALLOC(e->d_subs, sizeof(FbSub) * (size_t)e->max_subs);
+    FB_TRY_ALLOC(e->d_modes, (size_t)e->max_frames);
+    FB_TRY_ALLOC(e->d_smp, sizeof(int32_t) * nint);
+    FB_TRY_ALLOC(e->d_res, sizeof(int32_t) * nint);
+    FB_TRY_ALLOC(e->d_slots, e->slot_bytes);
+    FB_TRY_ALLOC(e->d_frame_len, sizeof(uint32_t) * (size_t)e->max_frames);
+    FB_TRY_ALLOC(e->d_frame_off, sizeof(uint64_t) * (size_t)e->max_frames);
+    if (cfg->prediction_type == 2) {
+        FB_TRY_ALLOC(e->d_coefs, sizeof(int32_t) * FB_MAX_ORDER * FB_MAX_ORDER * (size_t)e->max_subs);
+        FB_TRY_ALLOC(e->d_shifts, sizeof(int32_t) * FB_MAX_ORDER * (size_t)e->max_subs);
+    }
+    if (cfg->variable_block_size) {
+        FB_TRY_ALLOC(e->d_vbs_sizes, sizeof(uint32_t) * 8 * (size_t)max_blocks);
+        FB_TRY_ALLOC(e->d_vbs_counts, sizeof(uint32_t) * (size_t)max_blocks);
+    }
+
+    /* shared-memory staging where a whole block fits */
+    e->lpc_smem_doubles = ((size_t)(B + 1) * 8 <= FB_SMEM_BUDGET) ? B + 1 : 0;
+    e->search_smem_ints = ((size_t)B * 4 <= FB_SMEM_BUDGET) ? B : 0;
+    {
+        const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
+        const uint64_t capw = (capb + 3u) >> 2;
+        e->pack_smem_words = (capw * 4u <= FB_SMEM_BUDGET) ? (int)capw : 0;
+    }
+    if (cfg->prediction_type == 2 && !e->lpc_smem_doubles)
+        FB_TRY_ALLOC(e->d_win, sizeof(double) * (nint + e->max_subs + 16));
+    cudaFuncSetAttribute(k_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, e->lpc_smem_doubles * 8);
+    cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
+    cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, e->pack_smem_words * 4);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) { set_err(err, errlen, "cudaFuncSetAttribute failed", ce); fb_engine_destroy(e); return nullptr; }
+    return e;
+}
+
+extern "C" void fb_engine_destroy(FbEngine *e)
+{
+    if (!e) return;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_frames); cudaFree(e->d_nframes); cudaFree(e->d_subs); cudaFree(e->d_modes);
+    cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
+    cudaFree(e->d_win); cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
+    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" uint32_t fb_engine_max_blocks(const FbEngine *e) { return e ? e->max_blocks : 0; }
+extern "C" uint32_t fb_engine_max_frames(const FbEngine *e) { return e ? e->max_frames : 0; }
+extern "C" uint64_t fb_engine_out_capacity(const FbEngine *e) { return e ? e->out_bytes : 0; }
+extern "C" uint64_t fb_engine_launch_count(const FbEngine *e) { return e ? e->launches : 0; }
+extern "C" const char *fb_engine_last_error(const FbEngine *e) { return e ? e->err : "no engine"; }
+
+extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, uint64_t nsamples,
+                                       uint32_t first_number, void *d_out, uint32_t *d_frame_len,
+                                       uint32_t *d_frame_bs, FbSummary *d_summary, void *stream_v)
+{
+    if (!e || !d_pcm || !d_out || !d_summary) return -1;
+    if (nsamples == 0 || nsamples > e->max_samples) {
+        snprintf(e->err, sizeof e->err, "chunk of %llu samples exceeds capacity %llu",
+                 (unsigned long long)nsamples, (unsigned long long)e->max_samples);
+        return -2;
+    }
+    if (fmt < FB_PCM_S32 || fmt > FB_PCM_S8) return -3;
+    const FbConfig cfg = e->cfg;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : e->stream;
+    const uint32_t ns = (uint32_t)nsamples;
+    const uint32_t B = (uint32_t)cfg.block_size;
+    const uint32_t nblocks = (ns + B - 1) / B;
+    const uint32_t grid_frames = cfg.variable_block_size ? nblocks * 8u : nblocks;
+    const uint32_t grid_subs = grid_frames * (uint32_t)cfg.channels;
+    uint32_t *flen = d_frame_len ? d_frame_len : e->d_frame_len;
+
+    cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st);
+    if (cfg.variable_block_size) {
+        FB_LAUNCH(k_vbs_split, dim3(nblocks), dim3(FB_PREP_THREADS), 0, st,
+                  cfg, d_pcm, fmt, ns, e->d_vbs_sizes, e->d_vbs_counts);
+        FB_LAUNCH(k_frames_vbs, dim3(1), dim3(1024), 0, st,
+                  cfg, ns, first_number, e->d_vbs_sizes, e->d_vbs_counts, e->d_frames, e->d_nframes);
+        e->launches += 2;
+    } else {
+        FB_LAUNCH(k_frames_fixed, dim3((nblocks + 255) / 256), dim3(256), 0, st,
+                  cfg, ns, first_number, e->d_frames, e->d_nframes);
+        e->launches += 1;
+    }
+    FB_LAUNCH(k_prep, dim3(grid_frames), dim3(FB_PREP_THREADS), 0, st,
+              cfg, d_pcm, fmt, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_modes);
+    e->launches += 1;
+    if (cfg.prediction_type == 2) {
+        FB_LAUNCH(k_lpc, dim3(grid_subs), dim3(FB_LPC_THREADS), (size_t)e->lpc_smem_doubles * 8, st,
+                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts,
+                  e->d_win, e->lpc_smem_doubles);
+        e->launches += 1;
+    }
+    FB_LAUNCH(k_search, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
+              cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_coefs, e->d_shifts,
+              e->search_smem_ints);
+    FB_LAUNCH(k_pack, dim3(grid_frames), dim3(FB_PACK_THREADS), (size_t)e->pack_smem_words * 4, st,
+              cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
+              flen, d_frame_bs, e->d_verbatim, e->pack_smem_words);
+    FB_LAUNCH(k_offsets, dim3(1), dim3(1024), 0, st,
+              e->d_nframes, flen, e->d_frame_off, d_summary, e->d_verbatim);
+    FB_LAUNCH(k_compact, dim3(grid_frames), dim3(256), 0, st,
+              e->d_frames, e->d_nframes, flen, e->d_frame_off, e->d_slots, (uint8_t *)d_out);
+    e->launches += 4;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+        snprintf(e->err, sizeof e->err, "kernel launch failed: %s", cudaGetErrorString(ce));
+        return -4;
+    }
+    return 0;
+}
+
+extern "C" int fb_engine_read_subframes(FbEngine *e, FbSub *host, uint32_t max, void *stream_v)
+{
+    if (!e || !host) return -1;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : e->stream;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+    uint32_t nf = 0;
+    if (cudaMemcpy(&nf, e->d_nframes, sizeof nf, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    uint32_t ns = nf * (uint32_t)e->cfg.channels;
+    if (ns > max) ns = max;
+    if (cudaMemcpy(host, e->d_subs, sizeof(FbSub) * (size_t)ns, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    return (int)ns;
+}
+
+/* ---- thin runtime wrappers for the C host layer ------------------------- */
+extern "C" void *fb_cuda_malloc(size_t n) { void *p = nullptr; return cudaMalloc(&p, n) == cudaSuccess ? p : nullptr; }
+extern "C" void fb_cuda_free(void *p) { if (p) cudaFree(p); }
+extern "C" void *fb_cuda_malloc_host(size_t n) { void *p = nullptr; return cudaMallocHost(&p, n) == cudaSuccess ? p : nullptr; }
+extern "C" void fb_cuda_free_host(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void *fb_cuda_stream_create(void)
+{
+    cudaStream_t s = nullptr;
+    return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess ? (void *)s : nullptr;
+}
+extern "C" void fb_cuda_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+extern "C" int fb_cuda_stream_sync(void *s) { return cudaStreamSynchronize((cudaStream_t)s) == cudaSuccess ? 0 : -1; }
+extern "C" int fb_cuda_h2d(void *d, const void *h, size_t n, void *s)
+{
+    return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)s) == cudaSuccess ? 0 : -1;
+}
+extern "C" int fb_cuda_d2h(void *h, const void *d, size_t n, void *s)
+{
+    return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)s) == cudaSuccess ? 0 : -1;
+}
+extern "C" void *fb_cuda_event_create(void)
+{
+    cudaEvent_t ev = nullptr;
+    return cudaEventCreate(&ev) == cudaSuccess ? (void *)ev : nullptr;
+}
+extern "C" void fb_cuda_event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+extern "C" int fb_cuda_event_record(void *ev, void *s) { return cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)s) == cudaSuccess ? 0 : -1; }
+extern "C" int fb_cuda_event_sync(void *ev) { return cudaEventSynchronize((cudaEvent_t)ev) == cudaSuccess ? 0 : -1; }
+extern "C" int fb_cuda_stream_wait_event(void *s, void *ev) { return cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)ev, 0) == cudaSuccess ? 0 : -1; }
+extern "C" float fb_cuda_event_elapsed_ms(void *a, void *b)
+{
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) return -1.f;
+    return ms;
+}
+extern "C" int fb_cuda_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+extern "C" int fb_cuda_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -1; }

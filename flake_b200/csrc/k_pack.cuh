@@ -1,0 +1,448 @@
+/*
+ * k_pack.cuh -- parallel frame packer, one CTA per frame (encode.c:700-977,
+ * bitio.h, crc.c) plus the compaction of the staged frames into one
+ * contiguous byte stream.
+ *
+ * The reference writes a frame serially through a 32-bit accumulator.  Here
+ * every thread owns a contiguous run of samples of a subframe: it sizes its
+ * run's codes, a CTA-wide exclusive scan turns sizes into bit offsets, and the
+ * run is then emitted MSB-first into a zeroed staging buffer (whole words with
+ * plain stores, the two boundary words with atomicOr).  CRC-16 is computed in
+ * parallel over 32-bit words with slicing tables and the chunk CRCs are
+ * combined with x^(8*len) mod P multipliers (crc.c:24-92 defines P, init 0,
+ * no reflection).  The size check that forces VERBATIM subframes
+ * (encode.c:949-964) is evaluated on the exact byte count.
+ */
+#ifndef FLAKE_B200_K_PACK_CUH
+#define FLAKE_B200_K_PACK_CUH
+
+#include "dev_common.cuh"
+
+#define FB_PACK_THREADS 256
+
+/* ---------------- CRC helpers ---------------------------------------- */
+__device__ __forceinline__ uint32_t fb_crc16_byte(uint32_t crc, uint32_t byte)
+{
+    crc ^= byte << 8;
+    for (int b = 0; b < 8; b++)
+        crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x8005u) & 0xffffu : (crc << 1) & 0xffffu;
+    return crc;
+}
+__device__ __forceinline__ uint32_t fb_crc8_byte(uint32_t crc, uint32_t byte)
+{
+    crc ^= byte;
+    for (int b = 0; b < 8; b++)
+        crc = (crc & 0x80u) ? ((crc << 1) ^ 0x07u) & 0xffu : (crc << 1) & 0xffu;
+    return crc;
+}
+/* a * b mod (x^16 + x^15 + x^2 + 1) over GF(2) */
+__device__ __forceinline__ uint32_t fb_gf16_mul(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 15; i >= 0; i--) {
+        r = (r & 0x8000u) ? ((r << 1) ^ 0x8005u) & 0xffffu : (r << 1) & 0xffffu;
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+/* x^(8*nbytes) mod P */
+__device__ __forceinline__ uint32_t fb_gf16_xpow8(uint32_t nbytes)
+{
+    uint32_t result = 1, base = 0x0100u;      /* x^8 */
+    while (nbytes) {
+        if (nbytes & 1u) result = fb_gf16_mul(result, base);
+        base = fb_gf16_mul(base, base);
+        nbytes >>= 1;
+    }
+    return result;
+}
+
+/* ---------------- MSB-first bit emitter -------------------------------- */
+struct FbBitPut {
+    uint32_t *buf;      /* staging buffer as 32-bit words holding big-endian bytes */
+    uint32_t capw;      /* capacity in words */
+    uint32_t widx;      /* current word */
+    uint32_t cur;       /* bits gathered for the current word (MSB first) */
+    int fill;           /* bits of `cur` in use, 0..31 */
+    bool boundary;      /* current word may be shared with another thread */
+};
+
+__device__ __forceinline__ void fb_bp_init(FbBitPut &b, uint32_t *buf, uint32_t capw, uint64_t bitpos)
+{
+    b.buf = buf; b.capw = capw;
+    b.widx = (uint32_t)(bitpos >> 5);
+    b.fill = (int)(bitpos & 31u);
+    b.cur = 0;
+    b.boundary = true;
+}
+__device__ __forceinline__ void fb_bp_flush_word(FbBitPut &b, bool last)
+{
+    if (b.cur && b.widx < b.capw) {
+        const uint32_t be = __byte_perm(b.cur, 0, 0x0123);
+        if (b.boundary || last) atomicOr(&b.buf[b.widx], be);
+        else b.buf[b.widx] = be;
+    }
+    b.widx++; b.cur = 0; b.fill = 0; b.boundary = false;
+}
+/* nbits in 1..32, val < 2^nbits */
+__device__ __forceinline__ void fb_bp_put(FbBitPut &b, int nbits, uint32_t val)
+{
+    const int space = 32 - b.fill;
+    if (nbits < space) {
+        b.cur |= val << (space - nbits);
+        b.fill += nbits;
+    } else {
+        const int rem = nbits - space;
+        b.cur |= rem < 32 ? (val >> rem) : 0u;
+        fb_bp_flush_word(b, false);
+        if (rem) { b.cur = val << (32 - rem); b.fill = rem; }
+    }
+}
+__device__ __forceinline__ void fb_bp_skip(FbBitPut &b, uint32_t nzeros)
+{
+    uint64_t f = (uint64_t)b.fill + nzeros;
+    if (f >= 32) {
+        fb_bp_flush_word(b, false);
+        b.widx += (uint32_t)(f >> 5) - 1u;
+        f &= 31u;
+    }
+    b.fill = (int)f;
+}
+__device__ __forceinline__ void fb_bp_finish(FbBitPut &b)
+{
+    if (b.fill) fb_bp_flush_word(b, true);
+}
+__device__ __forceinline__ void fb_bp_put_signed(FbBitPut &b, int nbits, int32_t v)
+{
+    if (nbits >= 32) { fb_bp_put(b, 32, (uint32_t)v); return; }
+    fb_bp_put(b, nbits, (uint32_t)v & ((1u << nbits) - 1u));
+}
+
+/* ---------------- per-subframe geometry -------------------------------- */
+struct FbSubLayout {
+    int type, order, obits, wasted, shift, method, porder, psize, pbits;
+    uint32_t preamble_bits;     /* header + warm-up + coefficients + method/porder/param[0] */
+};
+
+__device__ __forceinline__ FbSubLayout fb_sub_layout(const FbSub *sb, int n, bool force_verbatim)
+{
+    FbSubLayout L;
+    L.type = force_verbatim ? 1 : sb->type;
+    L.order = sb->order; L.obits = sb->obits; L.wasted = sb->wasted; L.shift = sb->shift;
+    L.method = sb->method; L.porder = sb->porder;
+    L.psize = n >> L.porder;
+    L.pbits = 4 + L.method;
+    uint32_t pre = 8u + (uint32_t)L.wasted;         /* 0, 6-bit type, wasted flag [+ unary] */
+    if (L.type == 0) pre += (uint32_t)L.obits;
+    else if (L.type == 8)  pre += (uint32_t)(L.order * L.obits) + 6u + (uint32_t)L.pbits;
+    else if (L.type == 32) pre += (uint32_t)(L.order * L.obits) + 9u + (uint32_t)L.order * 15u + 6u + (uint32_t)L.pbits;
+    L.preamble_bits = pre;
+    return L;
+}
+
+/* bits of sample i's token (Rice code [+ partition parameter]) */
+__device__ __forceinline__ uint32_t fb_token_bits(const FbSubLayout &L, const FbSub *sb,
+                                                  const int32_t *data, int i)
+{
+    if (L.type == 1) return (uint32_t)L.obits;
+    if (L.type == 0 || i < L.order) return 0;
+    const int p = i / L.psize;
+    const int k = sb->params[p];
+    const uint32_t u = fb_zigzag(data[i]);
+    uint32_t bits = (u >> k) + 1u + (uint32_t)k;
+    if (p > 0 && i == p * L.psize) bits += (uint32_t)L.pbits;
+    return bits;
+}
+
+/*
+ * frames[f] -> staged bytes at slots + frames[f].slot, frame_len[f].
+ * smem_words: capacity of the dynamic shared staging buffer (0: write the
+ * global slot directly).
+ */
+__global__ void __launch_bounds__(FB_PACK_THREADS)
+k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
+       const int32_t *res, FbSub *subs, const uint8_t *ch_modes, uint8_t *slots,
+       uint32_t *frame_len, uint32_t *frame_bs, uint32_t *verbatim_count, int smem_words)
+{
+    FB_DYN_SMEM(dyn);
+    __shared__ uint32_t scan_scratch[33];
+    __shared__ uint16_t crc_tab[4][256];
+    __shared__ uint32_t crc_part[32];
+    __shared__ uint32_t s_hdr_len;
+    __shared__ uint8_t s_hdr[24];
+
+    const uint32_t f = blockIdx.x;
+    if (f >= *nframes) return;
+    const FbFrame fr = frames[f];
+    const int n = (int)fr.n, C = cfg.channels;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int vsize = fb_verbatim_size(cfg, n);
+    /* staging capacity: verbatim encoding plus header slack, see fb_slot_offset */
+    const uint32_t cap_bytes = 64u + (uint32_t)(((uint64_t)n * (uint64_t)(C * cfg.bps + 1) + 7u) >> 3);
+    const uint32_t capw = (cap_bytes + 3u) >> 2;
+    uint32_t *gslot = (uint32_t *)(slots + fr.slot);
+    const bool in_smem = capw <= (uint32_t)smem_words;
+    uint32_t *wbuf = in_smem ? (uint32_t *)dyn : gslot;
+
+    /* slicing tables: tab[t][b] = CRC-16 of byte b followed by t zero bytes */
+    for (int b = tid; b < 256; b += T) {
+        uint32_t c = fb_crc16_byte(0, (uint32_t)b);
+        crc_tab[0][b] = (uint16_t)c;
+        c = fb_crc16_byte(c, 0); crc_tab[1][b] = (uint16_t)c;
+        c = fb_crc16_byte(c, 0); crc_tab[2][b] = (uint16_t)c;
+        c = fb_crc16_byte(c, 0); crc_tab[3][b] = (uint16_t)c;
+    }
+
+    /* ---- frame header, encode.c:718-764 (thread 0, byte granular) -------- */
+    if (tid == 0) {
+        int bs0 = -1, bs1 = -1;
+        const int tab[15] = {0, 192, 576, 1152, 2304, 4608, 0, 0, 256, 512, 1024, 2048, 4096, 8192, 16384};
+        for (int i = 0; i < 15; i++) if (n == tab[i]) { bs0 = i; break; }
+        if (bs0 < 0) { bs0 = n <= 256 ? 6 : 7; bs1 = n - 1; }
+        const int mode = ch_modes[f];
+        int h = 0;
+        s_hdr[h++] = 0xff;
+        s_hdr[h++] = (uint8_t)(0xf8 | (cfg.allow_vbs ? 1 : 0));
+        s_hdr[h++] = (uint8_t)((bs0 << 4) | cfg.sr_code0);
+        s_hdr[h++] = (uint8_t)(((mode == 0 ? C - 1 : mode) << 4) | (cfg.bps_code << 1));
+        /* write_utf8, encode.c:700-716 */
+        const uint32_t v = fr.number;
+        if (v < 0x80u) {
+            s_hdr[h++] = (uint8_t)v;
+        } else {
+            const int bytes = (fb_ilog2(v) + 4) / 5;
+            int sh = (bytes - 1) * 6;
+            s_hdr[h++] = (uint8_t)((256 - (256 >> bytes)) | (v >> sh));
+            while (sh >= 6) { sh -= 6; s_hdr[h++] = (uint8_t)(0x80u | ((v >> sh) & 0x3fu)); }
+        }
+        if (bs1 >= 0) {
+            if (bs1 < 256) s_hdr[h++] = (uint8_t)bs1;
+            else { s_hdr[h++] = (uint8_t)(bs1 >> 8); s_hdr[h++] = (uint8_t)bs1; }
+        }
+        if (cfg.sr_code1 > 0) {
+            if (cfg.sr_code1 < 256) s_hdr[h++] = (uint8_t)cfg.sr_code1;
+            else { s_hdr[h++] = (uint8_t)(cfg.sr_code1 >> 8); s_hdr[h++] = (uint8_t)cfg.sr_code1; }
+        }
+        uint32_t crc = 0;
+        for (int i = 0; i < h; i++) crc = fb_crc8_byte(crc, s_hdr[i]);
+        s_hdr[h++] = (uint8_t)crc;
+        s_hdr_len = (uint32_t)h;
+    }
+    __syncthreads();
+    const uint32_t hdr_len = s_hdr_len;
+
+    const int R = (n + T - 1) / T;                  /* samples per thread run */
+    const int i0 = min(n, tid * R), i1 = min(n, i0 + R);
+
+    uint64_t total_bits = 0;
+    bool verbatim = false;
+    for (int pass = 0; pass < 2; pass++) {
+        /* zero the staging buffer */
+        for (uint32_t w = tid; w < capw; w += T) wbuf[w] = 0;
+        __syncthreads();
+        uint64_t bitpos = (uint64_t)hdr_len * 8u;
+        if (tid == 0) {
+            FbBitPut b; fb_bp_init(b, wbuf, capw, 0);
+            for (uint32_t i = 0; i < hdr_len; i++) fb_bp_put(b, 8, s_hdr[i]);
+            fb_bp_finish(b);
+        }
+        for (int c = 0; c < C; c++) {
+            const FbSub *sb = &subs[(size_t)f * C + c];
+            const FbSubLayout L = fb_sub_layout(sb, n, verbatim);
+            const size_t off = (size_t)fr.start * C + (size_t)c * n;
+            const int32_t *data = (L.type == 1 || L.type == 0) ? smp + off : res + off;
+
+            /* size my run, scan */
+            uint32_t mybits = 0;
+            if (L.type == 1) mybits = (uint32_t)(i1 - i0) * (uint32_t)L.obits;
+            else if (L.type != 0)
+                for (int i = i0; i < i1; i++) mybits += fb_token_bits(L, sb, data, i);
+            uint32_t sub_tokens;
+            const uint32_t myoff = fb_block_exscan_u32(mybits, scan_scratch, &sub_tokens);
+
+            /* preamble (thread 0) */
+            if (tid == 0) {
+                FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos);
+                int code = L.type;
+                if (L.type == 8) code = 8 | L.order;
+                if (L.type == 32) code = 32 | (L.order - 1);
+                fb_bp_put(b, 7, (uint32_t)code);             /* leading 0 + 6-bit type */
+                if (L.wasted) { fb_bp_put(b, 1, 1); fb_bp_skip(b, (uint32_t)(L.wasted - 1)); fb_bp_put(b, 1, 1); }
+                else fb_bp_put(b, 1, 0);
+                if (L.type == 0) {
+                    fb_bp_put_signed(b, L.obits, sb->first);
+                } else if (L.type == 8 || L.type == 32) {
+                    for (int i = 0; i < L.order; i++) fb_bp_put_signed(b, L.obits, data[i]);
+                    if (L.type == 32) {
+                        fb_bp_put(b, 4, 14);
+                        fb_bp_put_signed(b, 5, L.shift);
+                        for (int i = 0; i < L.order; i++) fb_bp_put_signed(b, 15, sb->coefs[i]);
+                    }
+                    fb_bp_put(b, 2, (uint32_t)L.method);
+                    fb_bp_put(b, 4, (uint32_t)L.porder);
+                    fb_bp_put(b, L.pbits, sb->params[0]);
+                }
+                fb_bp_finish(b);
+            }
+            /* my tokens */
+            if (mybits) {
+                FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos + L.preamble_bits + myoff);
+                if (L.type == 1) {
+                    for (int i = i0; i < i1; i++) fb_bp_put_signed(b, L.obits, data[i]);
+                } else {
+                    for (int i = max(i0, L.order); i < i1; i++) {
+                        const int p = i / L.psize;
+                        const int k = sb->params[p];
+                        if (p > 0 && i == p * L.psize) fb_bp_put(b, L.pbits, (uint32_t)k);
+                        const uint32_t u = fb_zigzag(data[i]);
+                        fb_bp_skip(b, u >> k);
+                        fb_bp_put(b, k + 1, (1u << k) | (u & ((1u << k) - 1u)));
+                    }
+                }
+                fb_bp_finish(b);
+            }
+            bitpos += (uint64_t)L.preamble_bits + sub_tokens;
+        }
+        total_bits = bitpos;
+        const uint64_t nbytes = ((total_bits + 7u) >> 3) + 2u;
+        /* encode.c:949: eof (buffer = 3/2 verbatim size) or larger than the verbatim bound */
+        if (pass == 0 && nbytes > (uint64_t)vsize) {
+            verbatim = true;
+            __syncthreads();
+            continue;
+        }
+        break;
+    }
+    __syncthreads();
+
+    uint32_t body = (uint32_t)((total_bits + 7u) >> 3);      /* bytes before the CRC-16 */
+    if (body + 2u > cap_bytes) body = cap_bytes - 2u;         /* cannot happen for <= 24-bit input */
+
+    /* ---- CRC-16 over the body: right-aligned word chunks ------------------- */
+    {
+        const uint32_t nwords = (body + 3u) >> 2;            /* trailing pad bytes are zero... */
+        const uint32_t padbytes = nwords * 4u - body;        /* ...so treat them as leading zeros */
+        /* chunking is done on a byte stream shifted right by padbytes: equivalent to
+         * prepending zero bytes, which leave a zero-initialised CRC unchanged. */
+        const uint32_t per = (nwords + (uint32_t)T - 1u) / (uint32_t)T;   /* words per thread */
+        const uint32_t lead = per * (uint32_t)T - nwords;                 /* virtual zero words in front */
+        uint32_t crc = 0;
+        for (uint32_t j = 0; j < per; j++) {
+            const uint32_t vw = (uint32_t)tid * per + j;                  /* virtual word index */
+            if (vw < lead) continue;
+            const uint32_t wi = vw - lead;                                /* index in shifted stream */
+            /* shifted stream word wi = bytes [4*wi - padbytes, 4*wi - padbytes + 4) of the body */
+            uint32_t word;
+            if (padbytes == 0) {
+                word = __byte_perm(wbuf[wi], 0, 0x0123);
+            } else {
+                const uint32_t hi = wi ? __byte_perm(wbuf[wi - 1], 0, 0x0123) : 0u;
+                const uint32_t lo = __byte_perm(wbuf[wi], 0, 0x0123);
+                word = (hi << (32u - 8u * padbytes)) | (lo >> (8u * padbytes));
+            }
+            const uint32_t x = word ^ (crc << 16);
+            crc = (uint32_t)crc_tab[3][x >> 24] ^ (uint32_t)crc_tab[2][(x >> 16) & 255u] ^
+                  (uint32_t)crc_tab[1][(x >> 8) & 255u] ^ (uint32_t)crc_tab[0][x & 255u];
+        }
+        /* combine: thread t is followed by (T-1-t) chunks of `per` words */
+        uint32_t m = fb_gf16_xpow8(per * 4u);
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t right = __shfl_down_sync(FB_FULL_MASK, crc, o);
+            if ((lane & (2 * o - 1)) == 0) crc = fb_gf16_mul(crc, m) ^ right;
+            m = fb_gf16_mul(m, m);
+        }
+        if (lane == 0) crc_part[warp] = crc;
+        __syncthreads();
+        if (tid == 0) {
+            const int nw = T >> 5;
+            uint32_t acc = 0;
+            for (int w = 0; w < nw; w++) acc = fb_gf16_mul(acc, m) ^ crc_part[w];
+            /* append big-endian */
+            FbBitPut b; fb_bp_init(b, wbuf, capw, (uint64_t)body * 8u);
+            fb_bp_put(b, 16, acc);
+            fb_bp_finish(b);
+        }
+        __syncthreads();
+    }
+
+    const uint32_t nbytes = body + 2u;
+    if (in_smem) {
+        const uint32_t nw = (nbytes + 3u) >> 2;
+        for (uint32_t w = tid; w < nw; w += T) gslot[w] = wbuf[w];
+    }
+    if (tid == 0) {
+        frame_len[f] = nbytes;
+        if (frame_bs) frame_bs[f] = (uint32_t)n;
+        if (verbatim) {
+            atomicAdd(verbatim_count, 1u);
+            for (int c = 0; c < C; c++) subs[(size_t)f * C + c].type = 1;
+        }
+    }
+}
+
+/* ---------------- compaction ------------------------------------------- */
+/* exclusive scan of frame_len -> frame_off, plus the chunk summary; one CTA */
+__global__ void __launch_bounds__(1024)
+k_offsets(const uint32_t *nframes, const uint32_t *frame_len, uint64_t *frame_off,
+          FbSummary *summary, const uint32_t *verbatim_count)
+{
+    __shared__ uint32_t scan_scratch[33];
+    __shared__ uint64_t red[32];
+    __shared__ unsigned long long carry;
+    const uint32_t nf = *nframes;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    uint32_t mymax = 0;
+    for (uint32_t base = 0; base < nf; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nf ? frame_len[i] : 0u;
+        mymax = max(mymax, v);
+        uint32_t total;
+        const uint32_t ex = fb_block_exscan_u32(v, scan_scratch, &total);
+        if (i < nf) frame_off[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    mymax = fb_block_max_u32(mymax, red);
+    if (threadIdx.x == 0) {
+        summary->nframes = nf;
+        summary->max_frame_bytes = mymax;
+        summary->total_bytes = carry;
+        summary->verbatim_frames = *verbatim_count;
+        summary->reserved = 0;
+    }
+}
+
+/* one CTA per frame: staged slot (16-byte aligned) -> out + frame_off (any alignment) */
+__global__ void __launch_bounds__(256)
+k_compact(const FbFrame *frames, const uint32_t *nframes, const uint32_t *frame_len,
+          const uint64_t *frame_off, const uint8_t *slots, uint8_t *out)
+{
+    const uint32_t f = blockIdx.x;
+    if (f >= *nframes) return;
+    const uint32_t len = frame_len[f];
+    const uint32_t *src = (const uint32_t *)(slots + frames[f].slot);
+    uint8_t *dst = out + frame_off[f];
+    const uint32_t mis = (uint32_t)((size_t)dst & 3u);
+    /* head bytes up to the first aligned destination word */
+    const uint32_t head = mis ? min(len, 4u - mis) : 0u;
+    if (threadIdx.x < head) dst[threadIdx.x] = ((const uint8_t *)src)[threadIdx.x];
+    if (len <= head) return;
+    uint32_t *dw = (uint32_t *)(dst + head);
+    const uint32_t body = len - head, nwords = body >> 2;
+    /* destination word j holds source bytes [head + 4j, head + 4j + 4) */
+    const uint32_t sel = head == 0 ? 0x3210u : head == 1 ? 0x4321u : head == 2 ? 0x5432u : 0x6543u;
+    for (uint32_t j = threadIdx.x; j < nwords; j += blockDim.x) {
+        const uint32_t a = src[j], b = head ? src[j + 1] : 0u;
+        dw[j] = __byte_perm(a, b, sel);
+    }
+    const uint32_t tail = body & 3u;
+    if (threadIdx.x < tail) {
+        const uint32_t k = head + nwords * 4u + threadIdx.x;
+        dst[k] = ((const uint8_t *)src)[k];
+    }
+}
+
+#endif

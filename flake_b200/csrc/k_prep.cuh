@@ -1,0 +1,289 @@
+/*
+ * k_prep.cuh -- frame table, VBS split decision and the per-frame "prepare"
+ * kernel: PCM ingest + deinterleave (encode.c:541-553), stereo decorrelation
+ * estimate and transform (encode.c:598-694), wasted bits (encode.c:558-593),
+ * CONSTANT detection (optimize.c:143-151).
+ *
+ * Data layout written here: for a frame starting at sample `start` with n
+ * samples and C channels, channel c's plane is the int32 run
+ *     smp[start*C + c*n .. start*C + (c+1)*n)
+ * so the planes of a chunk tile the scratch buffer exactly like the
+ * interleaved input does.
+ */
+#ifndef FLAKE_B200_K_PREP_CUH
+#define FLAKE_B200_K_PREP_CUH
+
+#include "dev_common.cuh"
+
+#define FB_PREP_THREADS 256
+
+/* staging-slot geometry: frame f of a chunk gets a slot that is large enough
+ * for its VERBATIM encoding (16-byte aligned, 96 bytes of header slack). */
+__host__ __device__ __forceinline__ uint32_t fb_slot_offset(uint32_t frame_index, uint32_t start,
+                                                            int channels, int bps)
+{
+    uint64_t bits = (uint64_t)start * (uint64_t)(channels * bps + 1);
+    return (uint32_t)(16u * (frame_index * 6u + (uint32_t)((bits + 127u) >> 7)));
+}
+
+/* fixed block size: frame f = block f (encode.c:979-1005 without VBS) */
+__global__ void k_frames_fixed(FbConfig cfg, uint32_t nsamples, uint32_t first_number,
+                               FbFrame *frames, uint32_t *nframes)
+{
+    const uint32_t B = (uint32_t)cfg.block_size;
+    const uint32_t nf = (nsamples + B - 1) / B;
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+        FbFrame fr;
+        fr.start = f * B;
+        fr.n = min(B, nsamples - fr.start);
+        fr.number = first_number + (cfg.allow_vbs ? fr.start : f);
+        fr.slot = fb_slot_offset(f, fr.start, cfg.channels, cfg.bps);
+        frames[f] = fr;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *nframes = nf;
+}
+
+/*
+ * VBS split decision, one CTA per block -- vbs.c:36-83.
+ * Writes sizes[block][8] (zero padded) and counts[block].
+ * Blocks that do not qualify (n % 8, n < 128: encode.c:997-998) get one frame.
+ */
+__global__ void __launch_bounds__(FB_PREP_THREADS)
+k_vbs_split(FbConfig cfg, const void *pcm, int fmt, uint32_t nsamples,
+            uint32_t *sizes, uint32_t *counts)
+{
+    __shared__ uint64_t red[32];
+    __shared__ long long energy[8];
+    const uint32_t B = (uint32_t)cfg.block_size;
+    const uint32_t blk = blockIdx.x;
+    const uint32_t start = blk * B;
+    if (start >= nsamples) return;
+    const uint32_t n = min(B, nsamples - start);
+    const int C = cfg.channels;
+    uint32_t *my_sizes = sizes + (size_t)blk * 8;
+
+    if ((n % 8u) != 0 || n < 128u) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 8; i++) my_sizes[i] = 0;
+            my_sizes[0] = n; counts[blk] = 1;
+        }
+        return;
+    }
+    const uint32_t sec = n / 8;
+    for (int s = 0; s < 8; s++) {
+        /* sum over channels and j = 2..sec-1 of |x[j] - 2x[j-1] + x[j-2]|, int32 wrap + abs(int) */
+        const size_t base = ((size_t)start + (size_t)s * sec) * (size_t)C;
+        const uint32_t items = (sec - 2) * (uint32_t)C;
+        uint64_t acc = 0;
+        for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+            const size_t idx = base + 2u * (uint32_t)C + it;      /* element (j, ch) with j >= 2 */
+            uint32_t x0 = (uint32_t)fb_load_pcm(pcm, fmt, idx);
+            uint32_t x1 = (uint32_t)fb_load_pcm(pcm, fmt, idx - (size_t)C);
+            uint32_t x2 = (uint32_t)fb_load_pcm(pcm, fmt, idx - 2 * (size_t)C);
+            int32_t v = (int32_t)(x0 - 2u * x1 + x2);
+            int32_t a = v < 0 ? (int32_t)(0u - (uint32_t)v) : v;
+            acc += (uint64_t)(int64_t)a;
+        }
+        acc = fb_block_sum_u64(acc, red);
+        if (threadIdx.x == 0) energy[s] = (long long)acc / C + 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int nf = 0;
+        for (int s = 0; s < 8; s++) {
+            bool begin = (s == 0);
+            if (s > 0) {
+                /* abs() on a truncated int and a 32-bit multiply */
+                int32_t t = (int32_t)(uint32_t)(uint64_t)(energy[s - 1] - energy[s]);
+                int32_t a = t < 0 ? (int32_t)(0u - (uint32_t)t) : t;
+                int32_t prod = (int32_t)((uint32_t)a * 200u);
+                begin = ((long long)prod / energy[s - 1]) > 50;
+            }
+            if (begin) nf++;
+            out[nf - 1] += sec;
+        }
+        if (nf <= 1) { out[0] = n; nf = 1; for (int i = 1; i < 8; i++) out[i] = 0; }
+        for (int i = 0; i < 8; i++) my_sizes[i] = out[i];
+        counts[blk] = (uint32_t)nf;
+    }
+}
+
+/* frame table from the per-block split: single CTA, serial over warps' chunks */
+__global__ void __launch_bounds__(1024)
+k_frames_vbs(FbConfig cfg, uint32_t nsamples, uint32_t first_number,
+             const uint32_t *sizes, const uint32_t *counts, FbFrame *frames, uint32_t *nframes)
+{
+    __shared__ uint32_t scan_scratch[33];
+    __shared__ uint32_t carry;
+    const uint32_t B = (uint32_t)cfg.block_size;
+    const uint32_t nblocks = (nsamples + B - 1) / B;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblocks; base += blockDim.x) {
+        const uint32_t blk = base + threadIdx.x;
+        const uint32_t cnt = blk < nblocks ? counts[blk] : 0u;
+        uint32_t total;
+        const uint32_t ex = fb_block_exscan_u32(cnt, scan_scratch, &total);
+        const uint32_t first = carry + ex;
+        if (blk < nblocks) {
+            uint32_t start = blk * B;
+            for (uint32_t j = 0; j < cnt; j++) {
+                FbFrame fr;
+                fr.start = start;
+                fr.n = sizes[(size_t)blk * 8 + j];
+                fr.number = first_number + (cfg.allow_vbs ? start : first + j);
+                fr.slot = fb_slot_offset(first + j, start, cfg.channels, cfg.bps);
+                frames[first + j] = fr;
+                start += fr.n;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nframes = carry;
+}
+
+/* ------------------------------------------------------------------ */
+/* prepare: one CTA per frame                                           */
+/* ------------------------------------------------------------------ */
+__global__ void __launch_bounds__(FB_PREP_THREADS)
+k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint32_t *nframes,
+       int32_t *smp, FbSub *subs, uint8_t *ch_modes)
+{
+    __shared__ uint64_t red[32];
+    __shared__ int s_mode;
+    const uint32_t f = blockIdx.x;
+    if (f >= *nframes) return;
+    const FbFrame fr = frames[f];
+    const int n = (int)fr.n, C = cfg.channels;
+    const size_t ibase = (size_t)fr.start * (size_t)C;      /* interleaved index of sample 0 */
+    int32_t *plane = smp + ibase;
+    const int tid = threadIdx.x, T = blockDim.x;
+
+    /* ---- stereo mode estimate, encode.c:598-643 ---------------------- */
+    int mode = 0;                                            /* NOT_STEREO */
+    if (C == 2) {
+        mode = 1;                                            /* LEFT_RIGHT */
+        if (n > 32 && cfg.stereo_method == 1) {
+            uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (int i = 2 + tid; i < n; i += T) {
+                const size_t p = ibase + 2 * (size_t)i;
+                int32_t l0 = fb_load_pcm(pcm, fmt, p),     r0 = fb_load_pcm(pcm, fmt, p + 1);
+                int32_t l1 = fb_load_pcm(pcm, fmt, p - 2), r1 = fb_load_pcm(pcm, fmt, p - 1);
+                int32_t l2 = fb_load_pcm(pcm, fmt, p - 4), r2 = fb_load_pcm(pcm, fmt, p - 3);
+                int32_t lt = (int32_t)((uint32_t)l0 - 2u * (uint32_t)l1 + (uint32_t)l2);
+                int32_t rt = (int32_t)((uint32_t)r0 - 2u * (uint32_t)r1 + (uint32_t)r2);
+                int32_t m = (int32_t)((uint32_t)lt + (uint32_t)rt) >> 1;
+                int32_t d = (int32_t)((uint32_t)lt - (uint32_t)rt);
+                s0 += (uint64_t)(int64_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
+                s1 += (uint64_t)(int64_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
+                s2 += (uint64_t)(int64_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);
+                s3 += (uint64_t)(int64_t)(d < 0 ? (int32_t)(0u - (uint32_t)d) : d);
+            }
+            s0 = fb_block_sum_u64(s0, red);
+            s1 = fb_block_sum_u64(s1, red);
+            s2 = fb_block_sum_u64(s2, red);
+            s3 = fb_block_sum_u64(s3, red);
+            if (tid == 0) {
+                uint64_t s[4] = {s0, s1, s2, s3}, score[4];
+                for (int i = 0; i < 4; i++) {
+                    /* k from the uint32-truncated search, cost kept in uint64 (encode.c:617-620) */
+                    const uint64_t two = 2 * s[i];
+                    int best = 0; uint32_t bb = 0xffffffffu;
+                    for (int k = 0; k <= 30; k++) {
+                        uint32_t b = (uint32_t)fb_rice_count64(two, n, k);
+                        if (b < bb) { bb = b; best = k; }
+                    }
+                    s[i] = fb_rice_count64(two, n, best);
+                }
+                score[0] = s[0] + s[1]; score[1] = s[0] + s[3];
+                score[2] = s[1] + s[3]; score[3] = s[2] + s[3];
+                int best = 0;
+                for (int i = 1; i < 4; i++) if (score[i] < score[best]) best = i;
+                s_mode = best == 0 ? 1 : (best == 1 ? 8 : (best == 2 ? 9 : 10));
+            }
+            __syncthreads();
+            mode = s_mode;
+        }
+    }
+
+    /* ---- deinterleave + decorrelate, gather plane statistics ----------- */
+    uint32_t orv[FB_MAX_CH_UNROLL], mx[FB_MAX_CH_UNROLL], ne[FB_MAX_CH_UNROLL];
+    int32_t first[FB_MAX_CH_UNROLL];
+#pragma unroll
+    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) { orv[c] = 0; mx[c] = 0; ne[c] = 0; first[c] = 0; }
+
+    if (C == 2) {
+        int32_t l = fb_load_pcm(pcm, fmt, ibase), r = fb_load_pcm(pcm, fmt, ibase + 1);
+        if (mode == 10)     { first[0] = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; first[1] = (int32_t)((uint32_t)l - (uint32_t)r); }
+        else if (mode == 8) { first[0] = l; first[1] = (int32_t)((uint32_t)l - (uint32_t)r); }
+        else if (mode == 9) { first[0] = (int32_t)((uint32_t)l - (uint32_t)r); first[1] = r; }
+        else                { first[0] = l; first[1] = r; }
+        for (int i = tid; i < n; i += T) {
+            l = fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)i);
+            r = fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)i + 1);
+            int32_t a, b;
+            if (mode == 10)     { a = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; b = (int32_t)((uint32_t)l - (uint32_t)r); }
+            else if (mode == 8) { a = l; b = (int32_t)((uint32_t)l - (uint32_t)r); }
+            else if (mode == 9) { a = (int32_t)((uint32_t)l - (uint32_t)r); b = r; }
+            else                { a = l; b = r; }
+            plane[i] = a; plane[n + i] = b;
+            orv[0] |= (uint32_t)a; orv[1] |= (uint32_t)b;
+            ne[0] |= (uint32_t)(a != first[0]); ne[1] |= (uint32_t)(b != first[1]);
+            mx[0] = max(mx[0], (uint32_t)(a < 0 ? ~a : a)); mx[1] = max(mx[1], (uint32_t)(b < 0 ? ~b : b));
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < FB_MAX_CH_UNROLL; c++)
+            if (c < C) first[c] = fb_load_pcm(pcm, fmt, ibase + c);
+        for (int i = tid; i < n; i += T) {
+#pragma unroll
+            for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
+                if (c < C) {
+                    int32_t a = fb_load_pcm(pcm, fmt, ibase + (size_t)i * C + c);
+                    plane[(size_t)c * n + i] = a;
+                    orv[c] |= (uint32_t)a;
+                    ne[c] |= (uint32_t)(a != first[c]);
+                    mx[c] = max(mx[c], (uint32_t)(a < 0 ? ~a : a));
+                }
+            }
+        }
+    }
+
+    /* ---- wasted bits (encode.c:558-593) + subframe records -------------- */
+#pragma unroll
+    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
+        if (c < C) {
+            const uint32_t o = fb_block_or_u32(orv[c], red);
+            const uint32_t nz = fb_block_or_u32(ne[c], red);
+            const uint32_t m = fb_block_max_u32(mx[c], red);
+            int wasted = 0;
+            if (o) {
+                wasted = __ffs((int)o) - 1;
+                if (wasted >= cfg.bps - 1) wasted = 0;
+            }
+            if (wasted) {
+                int32_t *pl = plane + (size_t)c * n;
+                for (int i = tid; i < n; i += T) pl[i] >>= wasted;   /* own elements only */
+            }
+            if (tid == 0) {
+                FbSub *sb = &subs[(size_t)f * C + c];
+                int obits = cfg.bps;
+                if ((mode == 10 || mode == 8) && c == 1) obits++;
+                if (mode == 9 && c == 0) obits++;
+                sb->obits = obits - wasted;
+                sb->wasted = wasted;
+                sb->is_const = nz ? 0 : 1;
+                sb->first = first[c] >> wasted;
+                sb->maxabs = (m >> wasted) + 1u;         /* bound on |sample| */
+                sb->type = -1; sb->order = 0; sb->shift = 0; sb->method = 0; sb->porder = 0;
+                sb->est_order = 0; sb->est_bits = 0;
+            }
+        }
+    }
+    if (tid == 0) ch_modes[f] = (uint8_t)mode;
+}
+
+#endif

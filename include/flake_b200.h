@@ -1,0 +1,123 @@
+/*
+ * flake_b200.h -- batch and device-resident entry points, exported by
+ * libflake.so IN ADDITION to the unchanged flake.h API.
+ *
+ * Why they exist: flake_encode_frame (libflake/encode.c:979-1008) hands the
+ * encoder ONE block per synchronous call, and the caller cannot supply block
+ * N+1 before the call for block N returns (flake/flake.c:624-663).  One 4096
+ * sample block is far too little work for a B200, so the per-block call is
+ * latency bound.  flake_b200_encode_stream takes any number of consecutive
+ * blocks and produces exactly the bytes the per-block loop would have
+ * produced, with the same effect on the context (frame counter, running
+ * maximum frame size, MD5 of the PCM).
+ *
+ * Each function states the reference interface it stands in for.
+ */
+#ifndef FLAKE_B200_H
+#define FLAKE_B200_H
+
+#include "flake.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* PCM container of the samples handed to the batch calls (always channel
+ * interleaved).  S32 is the flake_encode_frame convention (flake.h:225-226);
+ * the packed layouts are what libpcm_io reads from a WAV data chunk before it
+ * widens to int32 (libpcm_io/pcm_io.c:155-277) -- the widening then happens on
+ * the GPU. */
+enum {
+    FLAKE_B200_PCM_S32   = 0,
+    FLAKE_B200_PCM_S16LE = 1,
+    FLAKE_B200_PCM_S24LE = 2,
+    FLAKE_B200_PCM_S8    = 3
+};
+
+typedef struct FlakeB200Stats {
+    unsigned long long samples;         /* inter-channel samples encoded by the call      */
+    unsigned long long frames;
+    unsigned long long bytes;           /* frame bytes produced                            */
+    unsigned long long h2d_bytes;       /* host->device bytes copied                       */
+    unsigned long long d2h_bytes;       /* device->host bytes copied                       */
+    unsigned long long kernel_launches; /* CUDA kernels launched by the call               */
+    unsigned int max_frame_size;
+    unsigned int verbatim_frames;       /* frames that took the size fallback (encode.c:949) */
+    double gpu_ms;                      /* CUDA-event time of the call's kernels + copies  */
+    double md5_ms;                      /* host MD5 thread busy time                       */
+    double wall_ms;
+} FlakeB200Stats;
+
+/* Select the CUDA device used by contexts initialised afterwards (default:
+ * $FLAKE_B200_DEVICE, else the current device).  Returns 0 or -1. */
+FLAKE_API int flake_b200_set_device(int device);
+
+/* Blocks per engine pass of the batch calls (default $FLAKE_B200_CHUNK_BLOCKS or 2048). */
+FLAKE_API int flake_b200_set_chunk_blocks(FlakeContext *s, int blocks);
+
+/*
+ * Batch form of the flake/flake.c:624-663 loop over flake_encode_frame
+ * (encode.c:979-1008): encodes `nsamples` inter-channel samples as consecutive
+ * blocks of params.block_size (the last one may be short) from HOST memory and
+ * writes the frames back to back into `out` (host).  frame_len / frame_bs
+ * (optional, `frame_cap` entries) receive each frame's byte length and block
+ * size; *nframes the number of frames.  Updates the context exactly as the
+ * per-block calls would (frame counter, max frame size, MD5, last-block latch).
+ * Returns the number of bytes written, or a negative value:
+ *   -1 bad arguments / closed context / stream already ended with a short block
+ *   -2 output or frame arrays too small      -3 CUDA failure (see flake_b200_last_error)
+ */
+FLAKE_API long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int pcm_format,
+                                             unsigned long long nsamples,
+                                             unsigned char *out, unsigned long long out_cap,
+                                             unsigned int *frame_len, unsigned int *frame_bs,
+                                             unsigned int frame_cap, unsigned int *nframes);
+
+/* Upper bound of the bytes flake_b200_encode_stream can produce for nsamples. */
+FLAKE_API unsigned long long flake_b200_max_encoded_size(const FlakeContext *s,
+                                                         unsigned long long nsamples);
+
+/*
+ * Frame-range sharding: a frame's bytes depend only on its
+ * samples, the stream parameters and its header number (encode.c:726-764,
+ * 969-975), so a rank that encodes blocks [b0, b1) of a stream first seeks its
+ * context to the counter the serial encoder would have had there:
+ * b0 for fixed block size, b0*block_size samples when allow_vbs is set.
+ */
+FLAKE_API int flake_b200_seek(FlakeContext *s, unsigned int frame_counter);
+FLAKE_API unsigned int flake_b200_tell(const FlakeContext *s);
+
+/*
+ * Device-resident form: `d_pcm` and all outputs are DEVICE pointers, work is
+ * enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream)
+ * and the call returns without synchronising.  At most
+ * flake_b200_device_capacity() samples per call.  `d_summary` receives
+ * {uint32 nframes, uint32 max_frame_bytes, uint64 total_bytes, uint32
+ * verbatim_frames, uint32 0}.  Does not touch the context's MD5 or counters:
+ * `first_number` is the header number of the first frame.
+ * Returns 0 or a negative error.
+ */
+FLAKE_API int flake_b200_encode_device(FlakeContext *s, const void *d_pcm, int pcm_format,
+                                       unsigned long long nsamples, unsigned int first_number,
+                                       void *d_out, unsigned int *d_frame_len,
+                                       unsigned int *d_frame_bs, void *d_summary,
+                                       void *cuda_stream);
+/* capacity of one device call: samples, output bytes, frames */
+FLAKE_API int flake_b200_device_capacity(FlakeContext *s, unsigned long long *max_samples,
+                                         unsigned long long *out_bytes, unsigned int *max_frames);
+
+/* Per-subframe decisions of the most recent engine pass, for stage-level parity
+ * tests (type, order, shift, coefficients, Rice parameters: what FlacSubframe
+ * holds, encode.h:52-63).  `subs` is an array of `max` records of
+ * flake_b200_subframe_record_size() bytes.  Returns the record count. */
+FLAKE_API int flake_b200_last_subframes(FlakeContext *s, void *subs, unsigned int max);
+FLAKE_API unsigned int flake_b200_subframe_record_size(void);
+
+FLAKE_API int flake_b200_get_stats(const FlakeContext *s, FlakeB200Stats *stats);
+FLAKE_API const char *flake_b200_last_error(const FlakeContext *s);
+FLAKE_API const char *flake_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the flake_b200 FLAC encoding hot path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line on rank 0.  For N > 1 the driver launches it under
+torch.distributed.run, one rank per GPU.
+
+Workload (BASELINE.json configs[1], "C2"): flake -8 on a 1 h synthetic 16-bit
+stereo 44.1 kHz stream = 158,760,000 inter-channel samples, 38,760 blocks of 4096.
+A *step* is one pass of the hot path over that whole stream on every rank (each
+rank encodes its own stream: frames shard with no collective, weak scaling).
+
+  value  MSamples/s with the PCM already resident in HBM (packed s16le, the WAV
+         data layout), device-resident outputs, CUDA events on the launching
+         stream, max over ranks.
+  e2e    the same metric through the host-buffer C ABI (flake_b200_encode_stream
+         on int32 samples -- the flake_encode_frame convention): H2D, kernels,
+         D2H and the MD5 of the PCM all inside the timed region.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref
+compiled from the reference sources, else the oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_SAMPLES = 158_760_000          # 1 h at 44.1 kHz
+RATE, CHANNELS, BPS, LEVEL, BLOCK = 44100, 2, 16, 8, 4096
+HBM_FALLBACK_GBS = 6650.0         # B200_PROFILING.md fallback
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------
+# synthetic PCM of the C2 shape, generated on the device (fast, deterministic)
+# --------------------------------------------------------------------------
+def synth_device(nsamples: int, seed: int, device):
+    """(nsamples, 2) int16 on `device`: sines + chirp under an envelope, shaped
+    noise bursts, a white floor, sparse impulses, silence / DC / quiet stretches
+    (the recipe of flake_b200/synth.py)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(0xF1A4E000 + seed)
+    out = torch.empty((nsamples, 2), dtype=torch.int16, device=device)
+    seg = 1 << 22
+    full = 32767.0
+    rs = np.random.RandomState(seed + 12345)
+    freqs = rs.uniform(60.0, 5000.0, size=5)
+    amps = rs.uniform(0.03, 0.22, size=5)
+    phases = rs.uniform(0, 2 * np.pi, size=5)
+    env_f = rs.uniform(0.05, 0.4)
+    shift = int(rs.randint(1, 40))
+    prev_tail = None
+    for s0 in range(0, nsamples, seg):
+        n = min(seg, nsamples - s0)
+        t = (torch.arange(s0, s0 + n, device=device, dtype=torch.float64) / RATE)
+        x = torch.zeros(n, dtype=torch.float64, device=device)
+        for k in range(5):
+            if k == 0:
+                ph = 2 * np.pi * (freqs[0] * t + 0.5 * (freqs[0] * 0.8) * t * t / 3600.0)
+            else:
+                ph = 2 * np.pi * freqs[k] * t
+            x += amps[k] * torch.sin(ph + phases[k])
+        x *= (0.55 + 0.45 * torch.sin(2 * np.pi * env_f * t)) * full
+        noise = torch.randn(n, generator=g, device=device, dtype=torch.float32).double()
+        lp = noise.clone()
+        lp[1:] = 0.5 * noise[1:] + 0.5 * noise[:-1]
+        lp[2:] = 0.5 * lp[2:] + 0.5 * lp[:-2]
+        burst = ((torch.arange(s0, s0 + n, device=device) // 4096) % 9 == 0).double()
+        x += burst * 0.03 * full * lp + 0.003 * full * noise
+        imp = (torch.rand(n, generator=g, device=device) < 1.0 / 20000.0).double()
+        x += imp * (torch.rand(n, generator=g, device=device).double() - 0.5) * 1.2 * full
+        left = x
+        # right: delayed, attenuated copy + independent noise
+        src = torch.cat([prev_tail if prev_tail is not None else left[:shift] * 0, left])
+        right = 0.8 * src[:n] + 0.02 * full * torch.randn(n, generator=g, device=device).double()
+        prev_tail = left[-shift:].clone()
+        blk = torch.stack([left, right], dim=1)
+        # stretches of silence / DC / low level, a few seconds each, every ~3 min
+        pos = (torch.arange(s0, s0 + n, device=device) % (RATE * 180))
+        blk[(pos < RATE * 2)] = 0.0
+        blk[(pos >= RATE * 60) & (pos < RATE * 62)] = round(0.1 * full)
+        blk[(pos >= RATE * 120) & (pos < RATE * 123)] *= 0.05
+        out[s0:s0 + n] = torch.clamp(torch.round(blk), -32768, 32767).to(torch.int16)
+    return out
+
+
+# --------------------------------------------------------------------------
+# clocks sampler
+# --------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.index = index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for nme, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nme)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self.th.start()
+
+    def stop(self):
+        self._stop.set()
+        self.th.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+# --------------------------------------------------------------------------
+def cpu_encode_threads(pcm_i32: np.ndarray, threads: int, steps: int, warmup: int):
+    """Encode `threads` contiguous segments of pcm_i32 concurrently, one reference
+    context per thread (the reference API is single-threaded per context).
+    Returns (best MSamples/s, list of step seconds, kind)."""
+    from oracle import pyoracle as po
+    from flake_b200 import api
+    n = pcm_i32.shape[0]
+    seg = (n // threads) // BLOCK * BLOCK
+    kind = "reference" if po.have_ref() else "port"
+    ref = po.ref_library() if kind == "reference" else None
+
+    def work(t):
+        part = pcm_i32[t * seg:(t + 1) * seg]
+        if ref is not None:
+            api.encode_per_block(ref, part, RATE, BPS, LEVEL)
+        else:
+            po.encode_stream(part, RATE, BPS, LEVEL)
+
+    times = []
+    for it in range(warmup + steps):
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return seg * threads, times, kind
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from flake_b200 import synth
+    cores = os.cpu_count() or 1
+    threads = env_int("FLAKE_BENCH_REF_THREADS", cores)
+    per_thread = env_int("FLAKE_BENCH_REF_SAMPLES_PER_THREAD", BLOCK * 700)   # ~2.9 M samples, ~0.6 s of CPU
+    base = synth.synth_pcm(min(per_thread * threads, BLOCK * 700 * 4), CHANNELS, BPS, RATE, seed=0)
+    reps = (per_thread * threads + base.shape[0] - 1) // base.shape[0]
+    pcm = np.ascontiguousarray(np.tile(base, (reps, 1))[:per_thread * threads])
+    total, times, kind = cpu_encode_threads(pcm, threads, args.steps, max(1, min(args.warmup, 1)))
+    ms = 1e3 * float(np.mean(times))
+    val = total / (ms * 1e-3) / 1e6
+    sample = "%d threads x %d samples (%.0f s of audio each) of the C2 signal per step" % (
+        threads, total // threads, total / threads / RATE)
+    line = {
+        "impl": "reference", "metric": "MSamples/s encoded, flake -8", "value": round(val, 3),
+        "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": round(val, 3), "unit": "MSamples/s", "cores": threads, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": round(val, 3), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "audio_seconds_per_s": round(val * 1e6 / RATE, 1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "C2: flake -8 (LPC<=12 log search, Rice partition order 0..6, mid/side estimate), "
+                        "1 h 16-bit stereo 44.1 kHz = 158760000 samples, 38760 blocks of 4096, per GPU",
+            "level": LEVEL, "block_size": BLOCK, "channels": CHANNELS, "bits_per_sample": BPS,
+            "sample_rate": RATE, "samples_per_gpu": C2_SAMPLES,
+            "l2": "inputs (635 MB packed PCM per pass) larger than the 126 MB L2; no explicit flush",
+            "sharding": "one stream per rank, no collective" if n_gpus > 1 else "single stream"}
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from flake_b200 import api
+
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; flake_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    nsamples = env_int("FLAKE_BENCH_SAMPLES", C2_SAMPLES)
+    lib = api.load_library()
+    lib.flake_b200_set_device(local)
+    enc = api.Encoder(lib, CHANNELS, RATE, BPS, nsamples, LEVEL)
+    enc.init()
+    ctx = C.byref(enc.ctx)
+
+    # ---- inputs -------------------------------------------------------------
+    d_pcm = synth_device(nsamples, seed=rank, device=dev)              # packed s16le in HBM
+    cap_s, cap_b, cap_f = C.c_ulonglong(), C.c_ulonglong(), C.c_uint()
+    assert lib.flake_b200_device_capacity(ctx, C.byref(cap_s), C.byref(cap_b), C.byref(cap_f)) == 0
+    chunk = int(cap_s.value)
+    nchunks = (nsamples + chunk - 1) // chunk
+    d_out = torch.empty(int(cap_b.value), dtype=torch.uint8, device=dev)
+    d_flen = torch.empty(int(cap_f.value), dtype=torch.int32, device=dev)
+    d_sum = torch.zeros((nchunks, 3), dtype=torch.int64, device=dev)   # 24-byte FbSummary per chunk
+    # a real (non-default) torch stream: the library treats a NULL handle as "use the
+    # context's own stream", and torch events must see the stream the kernels run on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+
+    def device_pass():
+        for k in range(nchunks):
+            s0 = k * chunk
+            ns = min(chunk, nsamples - s0)
+            rc = lib.flake_b200_encode_device(
+                ctx, d_pcm[s0:].data_ptr(), api.PCM_S16LE, ns, s0 // BLOCK, d_out.data_ptr(),
+                d_flen.data_ptr(), None, d_sum[k].data_ptr(), stream.cuda_stream)
+            if rc:
+                raise RuntimeError("flake_b200_encode_device failed: %d" % rc)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        device_pass()
+    barrier()
+    st0 = enc.stats()
+    enc.set_profiling(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        device_pass()
+        ev[i + 1].record(stream)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    stages = enc.stage_times()
+    enc.set_profiling(False)
+    st1 = enc.stats()
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+    summ = d_sum.cpu().numpy().view(np.uint8).reshape(nchunks, 24)
+    frames = int(sum(int(np.frombuffer(summ[k, 0:4].tobytes(), np.uint32)[0]) for k in range(nchunks)))
+    out_bytes = int(sum(int(np.frombuffer(summ[k, 8:16].tobytes(), np.uint64)[0]) for k in range(nchunks)))
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * nsamples / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end-to-end through the host-buffer C ABI -----------------------------------
+    e2e_steps = max(1, min(args.steps, env_int("FLAKE_BENCH_E2E_STEPS", 3)))
+    h_pcm32 = torch.empty((nsamples, CHANNELS), dtype=torch.int32, pin_memory=True)
+    h_pcm32.copy_(d_pcm.to(torch.int32))
+    torch.cuda.synchronize()
+    pcm_np = h_pcm32.numpy()
+    cap = int(lib.flake_b200_max_encoded_size(ctx, nsamples))
+    h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    nblocks = (nsamples + BLOCK - 1) // BLOCK
+    h_flen = np.zeros(nblocks + 1, dtype=np.uint32)
+    nf = C.c_uint(0)
+    e2e_ms, e2e_bytes, md5_hex = [], 0, None
+    h2d = d2h = 0
+    enc2 = api.Encoder(lib, CHANNELS, RATE, BPS, nsamples, LEVEL)
+    enc2.init()
+    for it in range(1 + e2e_steps):
+        lib.flake_b200_reset_stream(C.byref(enc2.ctx))
+        barrier()
+        t0 = time.perf_counter()
+        rc = lib.flake_b200_encode_stream(C.byref(enc2.ctx), pcm_np.ctypes.data, api.PCM_S32, nsamples,
+                                          h_out.data_ptr(), cap, h_flen.ctypes.data, None,
+                                          nblocks + 1, C.byref(nf))
+        si, si_bytes = enc2.streaminfo()          # final STREAMINFO incl. MD5: the stream is complete
+        dt = time.perf_counter() - t0
+        if rc < 0:
+            raise RuntimeError("flake_b200_encode_stream failed: %d" % rc)
+        st = enc2.stats()
+        if it >= 1:
+            e2e_ms.append(dt * 1e3)
+            e2e_bytes, h2d, d2h = int(rc), int(st.h2d_bytes), int(st.d2h_bytes)
+            md5_hex = bytes(si.md5sum).hex()
+    enc2.close()
+    t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t.item())
+    e2e_value = world * nsamples / (e2e_ms_max * 1e-3) / 1e6
+
+    if rank != 0:
+        enc.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA events between kernels, timed region) ---
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    stage_ms = {k: v[0] for k, v in stages.items()}
+    stage_n = {k: v[1] for k, v in stages.items()}
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    dom_avg_ms = stage_ms[dom] / max(1, stage_n[dom])
+    # algorithmic bytes per launch: packed PCM in + FLAC frame bytes out,
+    # for the samples one launch (= one chunk) processes
+    bytes_per_sample = CHANNELS * 2 + out_bytes / float(nsamples)
+    samples_per_launch = nsamples / float(nchunks)
+    algo_bytes = bytes_per_sample * samples_per_launch
+    achieved = algo_bytes / (dom_avg_ms * 1e-3) / 1e9
+    ncu_traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ncu_traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": round(achieved, 2), "peak": peak_gbs,
+                "unit": "GB/s", "frac": round(achieved / peak_gbs, 5), "traffic": ncu_traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
+                "kernel_ms_per_launch": round(dom_avg_ms, 4),
+                "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
+                "stage_share": {k: round(v / max(1e-9, sum(stage_ms.values())), 4) for k, v in stage_ms.items()},
+                "note": "path is instruction-bound (integer/FP64 pipes), not HBM-bound; see DESIGN.md 6"}
+
+    # ---- CPU baseline: the compiled reference on one host core, bounded sample --------
+    cpu = None
+    try:
+        budget = env_int("FLAKE_BENCH_CPU_SAMPLES", BLOCK * 14000)       # 57 M samples ~ 10-15 s of CPU
+        budget = min(budget, nsamples // BLOCK * BLOCK)
+        total, times, kind = cpu_encode_threads(pcm_np[:budget], 1, 1, 0)
+        cpu = {"value": round(total / times[0] / 1e6, 3), "unit": "MSamples/s", "cores": 1, "kind": kind,
+               "sample": "first %d samples (%.0f s of audio) of rank 0's stream, one flake_encode_frame "
+                         "loop, 1 thread" % (total, total / RATE),
+               "host_cores_available": os.cpu_count()}
+    except Exception as exc:       # the baseline is informative; never fail the bench on it
+        cpu = {"value": None, "unit": "MSamples/s", "cores": 1, "kind": "unavailable", "sample": str(exc)}
+
+    line = {
+        "metric": "MSamples/s encoded, flake -8", "value": round(value, 2), "unit": "MSamples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": workload_config(world),
+        "audio_seconds_per_s": round(value * 1e6 / RATE, 1),
+        "e2e": {"value": round(e2e_value, 2), "unit": "MSamples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms_max, 2),
+                "input": "int32 interleaved host buffer (flake_encode_frame convention)",
+                "includes": "H2D, all kernels, D2H of frames+lengths, MD5 of the PCM, final STREAMINFO",
+                "md5": md5_hex},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "frames_per_step": frames, "compressed_bytes_per_step": out_bytes,
+        "compression_ratio": round(out_bytes / float(nsamples * CHANNELS * 2), 4),
+        "step_ms": [round(x, 2) for x in step_ms],
+    }
+    print(json.dumps(line), flush=True)
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

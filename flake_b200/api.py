@@ -24,6 +24,8 @@ DEFAULT_LIB = os.path.join(_HERE, "lib", "libflake.so")
 
 PCM_S32, PCM_S16LE, PCM_S24LE, PCM_S8 = 0, 1, 2, 3
 
+STAGES = ("frames", "prep", "lpc", "search", "pack", "offsets", "compact")
+
 ORDER_METHOD = {"max": 0, "est": 1, "2level": 2, "4level": 3, "8level": 4, "search": 5, "log": 6}
 
 
@@ -96,6 +98,7 @@ def load_library(path: Optional[str] = None, extension: bool = True) -> C.CDLL:
         lib.flake_b200_max_encoded_size.argtypes = [P(FlakeContext), C.c_ulonglong]
         lib.flake_b200_max_encoded_size.restype = C.c_ulonglong
         lib.flake_b200_seek.argtypes = [P(FlakeContext), C.c_uint]; lib.flake_b200_seek.restype = C.c_int
+        lib.flake_b200_reset_stream.argtypes = [P(FlakeContext)]; lib.flake_b200_reset_stream.restype = C.c_int
         lib.flake_b200_tell.argtypes = [P(FlakeContext)]; lib.flake_b200_tell.restype = C.c_uint
         lib.flake_b200_encode_device.argtypes = [P(FlakeContext), C.c_void_p, C.c_int, C.c_ulonglong, C.c_uint,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -105,6 +108,9 @@ def load_library(path: Optional[str] = None, extension: bool = True) -> C.CDLL:
         lib.flake_b200_last_subframes.argtypes = [P(FlakeContext), C.c_void_p, C.c_uint]
         lib.flake_b200_last_subframes.restype = C.c_int
         lib.flake_b200_subframe_record_size.argtypes = []; lib.flake_b200_subframe_record_size.restype = C.c_uint
+        lib.flake_b200_set_profiling.argtypes = [P(FlakeContext), C.c_int]; lib.flake_b200_set_profiling.restype = C.c_int
+        lib.flake_b200_stage_times.argtypes = [P(FlakeContext), P(C.c_double), P(C.c_ulonglong)]
+        lib.flake_b200_stage_times.restype = C.c_int
         lib.flake_b200_get_stats.argtypes = [P(FlakeContext), P(FlakeB200Stats)]; lib.flake_b200_get_stats.restype = C.c_int
         lib.flake_b200_last_error.argtypes = [P(FlakeContext)]; lib.flake_b200_last_error.restype = C.c_char_p
         lib.flake_b200_version.argtypes = []; lib.flake_b200_version.restype = C.c_char_p
@@ -212,6 +218,19 @@ class Encoder:
         if n < 0:
             raise FlakeLibraryError("flake_b200_last_subframes failed")
         return [arr[i] for i in range(n)]
+
+    def set_profiling(self, on: bool) -> None:
+        if self.lib.flake_b200_set_profiling(C.byref(self.ctx), 1 if on else 0):
+            raise FlakeLibraryError("flake_b200_set_profiling failed")
+
+    def stage_times(self):
+        """{stage: (cumulative ms, passes)} from CUDA events between the kernels."""
+        ms = (C.c_double * 7)()
+        cnt = (C.c_ulonglong * 7)()
+        n = self.lib.flake_b200_stage_times(C.byref(self.ctx), ms, cnt)
+        if n < 0:
+            raise FlakeLibraryError("flake_b200_stage_times failed")
+        return {STAGES[i]: (ms[i], cnt[i]) for i in range(n)}
 
     def stats(self) -> FlakeB200Stats:
         st = FlakeB200Stats()

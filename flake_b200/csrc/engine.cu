@@ -22,6 +22,7 @@
 #include <new>
 
 #define FB_SMEM_BUDGET (200 * 1024)
+#define FB_TIMING_RING 64
 
 struct FbEngine {
     FbConfig cfg;
@@ -43,6 +44,11 @@ struct FbEngine {
     uint32_t *d_vbs_sizes, *d_vbs_counts;
     int lpc_smem_doubles, search_smem_ints, pack_smem_words;
     uint64_t launches;
+    /* optional per-kernel CUDA-event timing (bench.py roofline) */
+    int timing_on, timing_passes;
+    cudaEvent_t tev[FB_TIMING_RING][FB_NUM_STAGES + 1];
+    double stage_ms[FB_NUM_STAGES];
+    uint64_t stage_launches[FB_NUM_STAGES];
     char err[256];
 };
 
@@ -142,6 +148,9 @@ extern "C" void fb_engine_destroy(FbEngine *e)
     cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
     cudaFree(e->d_win); cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
     cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts);
+    if (e->tev[0][0])
+        for (int p = 0; p < FB_TIMING_RING; p++)
+            for (int i = 0; i <= FB_NUM_STAGES; i++) cudaEventDestroy(e->tev[p][i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -172,7 +181,14 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     const uint32_t grid_subs = grid_frames * (uint32_t)cfg.channels;
     uint32_t *flen = d_frame_len ? d_frame_len : e->d_frame_len;
 
+    cudaEvent_t *tev = nullptr;
+    if (e->timing_on) {
+        if (e->timing_passes >= FB_TIMING_RING) fb_engine_collect_timing(e, nullptr, nullptr);
+        tev = e->tev[e->timing_passes++];
+    }
+#define FB_MARK(i) do { if (tev) cudaEventRecord(tev[(i)], st); } while (0)
     cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st);
+    FB_MARK(0);
     if (cfg.variable_block_size) {
         FB_LAUNCH(k_vbs_split, dim3(nblocks), dim3(FB_PREP_THREADS), 0, st,
                   cfg, d_pcm, fmt, ns, e->d_vbs_sizes, e->d_vbs_counts);
@@ -184,25 +200,33 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
                   cfg, ns, first_number, e->d_frames, e->d_nframes);
         e->launches += 1;
     }
+    FB_MARK(1);
     FB_LAUNCH(k_prep, dim3(grid_frames), dim3(FB_PREP_THREADS), 0, st,
               cfg, d_pcm, fmt, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_modes);
     e->launches += 1;
+    FB_MARK(2);
     if (cfg.prediction_type == 2) {
         FB_LAUNCH(k_lpc, dim3(grid_subs), dim3(FB_LPC_THREADS), (size_t)e->lpc_smem_doubles * 8, st,
                   cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts,
                   e->d_win, e->lpc_smem_doubles);
         e->launches += 1;
     }
+    FB_MARK(3);
     FB_LAUNCH(k_search, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
               cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_coefs, e->d_shifts,
               e->search_smem_ints);
+    FB_MARK(4);
     FB_LAUNCH(k_pack, dim3(grid_frames), dim3(FB_PACK_THREADS), (size_t)e->pack_smem_words * 4, st,
               cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
               flen, d_frame_bs, e->d_verbatim, e->pack_smem_words);
+    FB_MARK(5);
     FB_LAUNCH(k_offsets, dim3(1), dim3(1024), 0, st,
               e->d_nframes, flen, e->d_frame_off, d_summary, e->d_verbatim);
+    FB_MARK(6);
     FB_LAUNCH(k_compact, dim3(grid_frames), dim3(256), 0, st,
               e->d_frames, e->d_nframes, flen, e->d_frame_off, e->d_slots, (uint8_t *)d_out);
+    FB_MARK(7);
+#undef FB_MARK
     e->launches += 4;
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
@@ -210,6 +234,46 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
         return -4;
     }
     return 0;
+}
+
+extern "C" int fb_engine_set_timing(FbEngine *e, int on)
+{
+    if (!e) return -1;
+    if (on && !e->tev[0][0]) {
+        for (int p = 0; p < FB_TIMING_RING; p++)
+            for (int i = 0; i <= FB_NUM_STAGES; i++)
+                if (cudaEventCreate(&e->tev[p][i]) != cudaSuccess) return -2;
+    }
+    e->timing_on = on ? 1 : 0;
+    return 0;
+}
+
+/* Fold the recorded passes into the per-stage totals; optionally copy them out.
+ * Stages: 0 frame table (+VBS split), 1 prep, 2 lpc, 3 search, 4 pack, 5 offsets, 6 compact. */
+extern "C" int fb_engine_collect_timing(FbEngine *e, double *ms, uint64_t *launches)
+{
+    if (!e) return -1;
+    for (int p = 0; p < e->timing_passes; p++) {
+        cudaEventSynchronize(e->tev[p][FB_NUM_STAGES]);
+        for (int i = 0; i < FB_NUM_STAGES; i++) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, e->tev[p][i], e->tev[p][i + 1]) == cudaSuccess) {
+                e->stage_ms[i] += t;
+                e->stage_launches[i] += 1;
+            }
+        }
+    }
+    e->timing_passes = 0;
+    if (ms) for (int i = 0; i < FB_NUM_STAGES; i++) ms[i] = e->stage_ms[i];
+    if (launches) for (int i = 0; i < FB_NUM_STAGES; i++) launches[i] = e->stage_launches[i];
+    return FB_NUM_STAGES;
+}
+
+extern "C" void fb_engine_reset_timing(FbEngine *e)
+{
+    if (!e) return;
+    e->timing_passes = 0;
+    for (int i = 0; i < FB_NUM_STAGES; i++) { e->stage_ms[i] = 0; e->stage_launches[i] = 0; }
 }
 
 extern "C" int fb_engine_read_subframes(FbEngine *e, FbSub *host, uint32_t max, void *stream_v)
@@ -262,3 +326,17 @@ extern "C" float fb_cuda_event_elapsed_ms(void *a, void *b)
 }
 extern "C" int fb_cuda_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
 extern "C" int fb_cuda_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -1; }
+
+#ifdef FLAKE_B200_CUDA_EMU
+/* hooks for the host-side unit tests of device helpers (emulated build only) */
+extern "C" int fb_test_rice_k(uint64_t sum, int n) { return fb_rice_k(sum, n); }
+extern "C" int fb_test_limit_porder(int p, int n, int order) { return fb_limit_porder(p, n, order); }
+extern "C" uint32_t fb_test_crc16_words(const uint8_t *d, uint32_t n)
+{
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < n; i++) c = fb_crc16_byte(c, d[i]);
+    return c;
+}
+extern "C" uint32_t fb_test_gf16_xpow8(uint32_t nbytes) { return fb_gf16_xpow8(nbytes); }
+extern "C" uint32_t fb_test_gf16_mul(uint32_t a, uint32_t b) { return fb_gf16_mul(a, b); }
+#endif

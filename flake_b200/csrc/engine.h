@@ -98,6 +98,14 @@ int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, uint64_t ns
  * chunk to the host (synchronises the stream). */
 int fb_engine_read_subframes(FbEngine *e, FbSub *host, uint32_t max, void *stream);
 
+/* per-stage CUDA-event timing (events recorded on the launching stream between
+ * the kernels of a pass).  Stages: 0 frame table (+VBS split), 1 prep, 2 lpc,
+ * 3 search, 4 pack, 5 offsets, 6 compact. */
+#define FB_NUM_STAGES 7
+int  fb_engine_set_timing(FbEngine *e, int on);
+int  fb_engine_collect_timing(FbEngine *e, double *ms, uint64_t *launches);
+void fb_engine_reset_timing(FbEngine *e);
+
 /* kernels launched by this engine since creation (bench `gpu_launches`) */
 uint64_t fb_engine_launch_count(const FbEngine *e);
 const char *fb_engine_last_error(const FbEngine *e);

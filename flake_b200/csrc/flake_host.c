@@ -710,6 +710,19 @@ int flake_b200_seek(FlakeContext *s, unsigned int frame_counter)
     return 0;
 }
 
+int flake_b200_reset_stream(FlakeContext *s)
+{
+    if (!s || !s->private_ctx) return -1;
+    FbCtx *c = (FbCtx *)s->private_ctx;
+    c->frame_count = 0;
+    c->last_frame = 0;
+    fb_md5_init(&c->md5);
+    if (c->channels == 2) c->max_frame_size = 16 + ((c->cfg.block_size * (2 * c->bps + 1) + 7) >> 3);
+    else c->max_frame_size = 16 + ((c->cfg.block_size * c->channels * c->bps + 7) >> 3);
+    memset(&c->stats, 0, sizeof c->stats);
+    return 0;
+}
+
 unsigned int flake_b200_tell(const FlakeContext *s)
 {
     if (!s || !s->private_ctx) return 0;
@@ -745,6 +758,26 @@ int flake_b200_encode_device(FlakeContext *s, const void *d_pcm, int fmt, unsign
     c->stats.kernel_launches += fb_engine_launch_count(c->engN) - before;
     if (rc) snprintf(c->err, sizeof c->err, "%s", fb_engine_last_error(c->engN));
     return rc;
+}
+
+int flake_b200_set_profiling(FlakeContext *s, int on)
+{
+    if (!s || !s->private_ctx) return -1;
+    FbCtx *c = (FbCtx *)s->private_ctx;
+    if (flake_b200_device_capacity(s, NULL, NULL, NULL)) return -3;
+    if (on) fb_engine_reset_timing(c->engN);
+    return fb_engine_set_timing(c->engN, on);
+}
+
+int flake_b200_stage_times(FlakeContext *s, double *ms, unsigned long long *launches)
+{
+    if (!s || !s->private_ctx) return -1;
+    FbCtx *c = (FbCtx *)s->private_ctx;
+    if (!c->engN) return -1;
+    uint64_t l[FB_NUM_STAGES];
+    const int n = fb_engine_collect_timing(c->engN, ms, l);
+    if (launches) for (int i = 0; i < FB_NUM_STAGES; i++) launches[i] = l[i];
+    return n;
 }
 
 unsigned int flake_b200_subframe_record_size(void) { return (unsigned int)sizeof(FbSub); }

@@ -86,6 +86,11 @@ FLAKE_API unsigned long long flake_b200_max_encoded_size(const FlakeContext *s,
  */
 FLAKE_API int flake_b200_seek(FlakeContext *s, unsigned int frame_counter);
 FLAKE_API unsigned int flake_b200_tell(const FlakeContext *s);
+/* Start a new stream with the same parameters on an initialised context: frame
+ * counter 0, fresh MD5, max frame size back to the verbatim bound (the state
+ * flake_encode_init leaves, encode.c:446-469), statistics cleared.  Saves
+ * re-creating the GPU engine between files of one format. */
+FLAKE_API int flake_b200_reset_stream(FlakeContext *s);
 
 /*
  * Device-resident form: `d_pcm` and all outputs are DEVICE pointers, work is
@@ -112,6 +117,18 @@ FLAKE_API int flake_b200_device_capacity(FlakeContext *s, unsigned long long *ma
  * flake_b200_subframe_record_size() bytes.  Returns the record count. */
 FLAKE_API int flake_b200_last_subframes(FlakeContext *s, void *subs, unsigned int max);
 FLAKE_API unsigned int flake_b200_subframe_record_size(void);
+
+/*
+ * Per-stage device timing of the batch/device engine, measured with CUDA events
+ * recorded between the kernels on the launching stream.  Seven stages:
+ * 0 frame table (+VBS split), 1 prepare, 2 LPC analysis, 3 order/Rice search,
+ * 4 pack, 5 offsets scan, 6 compaction.  set_profiling(1) clears the totals;
+ * stage_times() synchronises the recorded events and returns cumulative
+ * milliseconds and pass counts per stage (arrays of 7).
+ */
+#define FLAKE_B200_NUM_STAGES 7
+FLAKE_API int flake_b200_set_profiling(FlakeContext *s, int on);
+FLAKE_API int flake_b200_stage_times(FlakeContext *s, double *ms, unsigned long long *launches);
 
 FLAKE_API int flake_b200_get_stats(const FlakeContext *s, FlakeB200Stats *stats);
 FLAKE_API const char *flake_b200_last_error(const FlakeContext *s);

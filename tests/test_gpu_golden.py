@@ -1,0 +1,127 @@
+"""CUDA path against the committed golden vectors (outputs of the compiled reference) and,
+at BASELINE.json sizes, through size-independent properties: encode -> decode round trip with
+every CRC-8 / CRC-16 and the STREAMINFO MD5 verified, frame accounting, per-block API ==
+batch API == frame-range-sharded encode."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from flake_b200 import api, shard, synth
+from test_oracle_golden import STREAMS, golden_pcm, GOLD
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rec", STREAMS, ids=[r["name"] for r in STREAMS])
+def test_gpu_reproduces_reference_files(rec, gpu_lib):
+    pcm = golden_pcm(rec)
+    got = api.encode_batch(gpu_lib, pcm, rec["rate"], rec["bps"], rec["level"], chunk_blocks=3,
+                           **rec["overrides"])
+    data = got.file_bytes()
+    assert len(got.frames) == rec["nframes"]
+    assert got.streaminfo.hex() == rec["streaminfo"]
+    assert len(data) == rec["flac_len"]
+    assert hashlib.sha256(data).hexdigest() == rec["flac_sha256"]
+    if "file" in rec:
+        with open(os.path.join(GOLD, rec["file"]), "rb") as f:
+            assert f.read() == data
+
+
+def _long_pcm(nsamples, channels, bps, rate, seed):
+    """A long stream assembled from a 40 s synthetic segment with per-tile gain, so that the
+    CPU-side generation stays cheap; every tile is still distinct data."""
+    base = synth.synth_pcm(min(nsamples, rate * 40), channels, bps, rate, seed=seed).astype(np.int64)
+    reps = (nsamples + base.shape[0] - 1) // base.shape[0]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tiles = []
+    for r in range(reps):
+        g = float(rng.uniform(0.3, 1.0))
+        tiles.append(np.rint(base * g).astype(np.int32))
+    return np.ascontiguousarray(np.concatenate(tiles)[:nsamples])
+
+
+@pytest.mark.parametrize("name,nsamples,ch,bps,rate,level", [
+    ("C1_10min_l5", 26_460_000, 2, 16, 44100, 5),
+    ("C2_10min_l8", 26_460_000, 2, 16, 44100, 8),
+    ("C3_2min_l12_s24_96k", 11_520_000, 2, 24, 96000, 12),
+    ("C4_1min_l9_8ch_s24", 2_880_000, 8, 24, 48000, 9),
+])
+def test_full_size_round_trip(name, nsamples, ch, bps, rate, level, gpu_lib, oracle):
+    pcm = _long_pcm(nsamples, ch, bps, rate, seed=level)
+    got = api.encode_batch(gpu_lib, pcm, rate, bps, level)
+    data = got.file_bytes()
+    dec, info = oracle.decode(data, max_samples=nsamples + 16)
+    assert info.md5_ok == 1, "STREAMINFO MD5 does not match the decoded PCM"
+    assert info.decoded_samples == nsamples and info.total_samples == nsamples
+    assert np.array_equal(dec, pcm)
+    assert int(np.sum(got.frame_bs)) == nsamples
+    bs = 8192 if level >= 11 else 4096
+    assert len(got.frames) >= (nsamples + bs - 1) // bs
+    # first blocks byte-identical to the oracle (the whole stream would take the CPU minutes)
+    k = bs * 64
+    want, flen, _, _ = oracle.encode_stream(pcm[:k], rate, bps, level)
+    assert got.payload[:len(want)] == want
+
+
+def test_c2_full_hour_linearity_of_sharding(gpu_lib):
+    """Frame-range independence at the full C2 length: encoding blocks [b0, b1) with a seeked
+    context equals the corresponding byte range of the whole-stream encode."""
+    n = 158_760_000
+    pcm = _long_pcm(n, 2, 16, 44100, seed=8)
+    whole = api.encode_batch(gpu_lib, pcm, 44100, 16, 8)
+    assert len(whole.frames) == 38760
+    lens = np.array(list(map(len, whole.frames)), dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    payload = whole.payload
+    for (b0, b1) in [(0, 100), (19380, 19480), (38700, 38760)]:
+        part = shard.encode_range(gpu_lib, pcm, 44100, 16, 8, b0, b1, n)
+        assert part[0] == payload[offs[b0]:offs[b1]]
+    # STREAMINFO: total samples and the MD5 of the raw little-endian PCM
+    assert whole.streaminfo[18:] == hashlib.md5(synth.pack_pcm(pcm, 16)).digest()
+
+
+def test_sharded_equals_single(gpu_lib, oracle):
+    pcm = synth.synth_pcm(4096 * 37 + 1200, 2, 16, 44100, seed=77, kind="impulses")
+    for level in (8, 9):
+        single = api.encode_batch(gpu_lib, pcm, 44100, 16, level).file_bytes()
+        n = pcm.shape[0]
+        nblocks = (n + 4095) // 4096
+        enc = api.Encoder(gpu_lib, 2, 44100, 16, n, level)
+        header = enc.init()
+        parts = [shard.encode_range(gpu_lib, pcm, 44100, 16, level, b0, b1, n)
+                 for (b0, b1) in shard.block_ranges(nblocks, 8)]
+        import ctypes as C
+        md5 = hashlib.md5(synth.pack_pcm(pcm, 16)).digest()
+
+        def si_fn(mx):
+            si = api.FlakeStreaminfo()
+            gpu_lib.flake_get_streaminfo(C.byref(enc.ctx), C.byref(si))
+            si.max_frame_size = max(int(si.max_frame_size), mx)
+            C.memmove(si.md5sum, md5, 16)
+            buf = (C.c_ubyte * 34)()
+            gpu_lib.flake_write_streaminfo(C.byref(si), buf)
+            return bytes(buf)
+        data, offsets, lens = shard.assemble(parts, header, si_fn)
+        enc.close()
+        assert data == single
+
+
+def test_unmodified_reference_cli_links_and_matches(gpu_lib, oracle, tmp_path):
+    """oracle/_ref/flake_cli_b200 = the reference's flake/flake.c + libpcm_io, UNCHANGED, linked
+    against flake_b200's libflake.so.  Its output must equal the reference CLI's."""
+    import subprocess
+    from oracle import pyoracle
+    cli = os.path.join(os.path.dirname(pyoracle.REF_SO), "flake_cli_b200")
+    if not os.path.exists(cli) or not os.path.exists(pyoracle.REF_CLI):
+        pytest.skip("oracle/_ref CLIs not built (needs /root/reference at build time)")
+    pcm = synth.synth_pcm(4096 * 5 + 3136, 2, 16, 44100, seed=4)
+    wav = tmp_path / "in.wav"
+    wav.write_bytes(synth.wav_bytes(pcm, 16, 44100))
+    for level in ("-5", "-8", "-9"):
+        a, b = tmp_path / "a.flac", tmp_path / "b.flac"
+        subprocess.run([cli, "-q", level, str(wav), "-o", str(a)], check=True)
+        subprocess.run([pyoracle.REF_CLI, "-q", level, str(wav), "-o", str(b)], check=True)
+        assert a.read_bytes() == b.read_bytes()

@@ -1,0 +1,92 @@
+"""Parity of the CUDA path (through the C ABI of flake_b200/lib/libflake.so) against the
+oracle restatement (and the compiled reference when oracle/_ref travelled with the repo).
+
+Bar: bit-exact frames, header and final STREAMINFO; the stream must also decode
+back to the input with all CRCs and the MD5 valid.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from flake_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # (name, nsamples, channels, bps, rate, kind, level, overrides)
+    ("l0_s16",   1152 * 9 + 77,  2, 16, 44100, "mix", 0, {}),
+    ("l1_s16",   1152 * 9 + 78,  2, 16, 44100, "mix", 1, {}),
+    ("l2_s16",   1152 * 9 + 80,  2, 16, 44100, "mix", 2, {}),
+    ("l3_s16",   4096 * 5 + 100, 2, 16, 44100, "mix", 3, {}),
+    ("l5_s16",   4096 * 9 + 3936 % 4096, 2, 16, 44100, "mix", 5, {}),
+    ("l6_s16",   4096 * 5 + 200, 2, 16, 44100, "mix", 6, {}),
+    ("l7_s16",   4096 * 5 + 300, 2, 16, 44100, "mix", 7, {}),
+    ("l8_s16",   4096 * 9 + 3136, 2, 16, 44100, "mix", 8, {}),
+    ("l9_s16",   4096 * 6, 2, 16, 44100, "impulses", 9, {}),
+    ("l10_s16",  4096 * 4, 2, 16, 44100, "impulses", 10, {}),
+    ("l11_s24",  8192 * 3 + 2048, 2, 24, 96000, "mix", 11, {}),
+    ("l12_s24",  8192 * 3 + 2048, 2, 24, 96000, "impulses", 12, {}),
+    ("l9_8ch",   4096 * 3 + 1024, 8, 24, 48000, "impulses", 9, {}),
+    ("l8_mono",  4096 * 3 + 10, 1, 16, 44100, "mix", 8, {}),
+    ("l8_noise", 4096 * 3, 2, 16, 44100, "noise", 8, {}),
+    ("l0_noise", 1152 * 5, 2, 16, 44100, "noise", 0, {}),
+    ("l5_wasted", 4096 * 3, 2, 16, 44100, "wasted", 5, {}),
+    ("l5_silence", 4096 * 3, 2, 16, 44100, "silence", 5, {}),
+    ("l8_tiny_tail", 4096 + 7, 2, 16, 44100, "mix", 8, {}),
+    ("l8_tail3", 4096 + 3, 2, 16, 44100, "mix", 8, {}),
+    ("l5_8bit", 4096 * 2 + 64, 2, 8, 22050, "mix", 5, {}),
+    ("l8_custom_rate", 4096 * 2, 2, 16, 37800, "mix", 8, {}),
+    ("l5_bs1000", 1000 * 5 + 10, 2, 16, 44100, "mix", 5, {"block_size": 1000}),
+    ("l8_max", 4096 * 2, 2, 16, 44100, "mix", 8, {"order_method": 0}),
+    ("l8_2level", 4096 * 2, 2, 16, 44100, "mix", 8, {"order_method": 2}),
+    ("l8_8level", 4096 * 2, 2, 16, 44100, "mix", 8, {"order_method": 4}),
+    ("l9_novbs", 4096 * 3, 2, 16, 44100, "mix", 9, {"variable_block_size": 0}),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_batch_matches_oracle(case, gpu_lib, oracle):
+    name, n, ch, bps, rate, kind, level, ov = case
+    pcm = synth.synth_pcm(n, ch, bps, rate, seed=zlib.crc32(name.encode()) % 1000, kind=kind)
+    got = api.encode_batch(gpu_lib, pcm, rate, bps, level, chunk_blocks=4, **ov)
+    want, flen, fbs, mx = oracle.encode_stream(pcm, rate, bps, level, **ov)
+    assert list(map(len, got.frames)) == list(flen)
+    assert list(got.frame_bs) == list(fbs)
+    assert got.payload == want
+    p = oracle.make_params(ch, rate, bps, level, n, **ov)
+    assert got.header == oracle.header(p)
+    assert got.streaminfo == oracle.streaminfo(p, mx, oracle.md5_pcm(pcm, bps))
+    dec, info = oracle.decode(got.file_bytes())
+    assert info.md5_ok == 1
+    assert np.array_equal(dec, pcm)
+
+
+@pytest.mark.parametrize("level", [0, 5, 8, 9])
+def test_per_block_api_matches_batch(level, gpu_lib):
+    pcm = synth.synth_pcm(4096 * 3 + 512, 2, 16, 44100, seed=7, kind="impulses")
+    a = api.encode_per_block(gpu_lib, pcm, 44100, 16, level)
+    b = api.encode_batch(gpu_lib, pcm, 44100, 16, level, chunk_blocks=2)
+    assert a.payload == b.payload
+    assert a.header == b.header and a.streaminfo == b.streaminfo
+
+
+@pytest.mark.parametrize("fmt,bps", [(api.PCM_S16LE, 16), (api.PCM_S24LE, 24)])
+def test_packed_pcm_ingest(fmt, bps, gpu_lib):
+    pcm = synth.synth_pcm(4096 * 2 + 100, 2, bps, 48000, seed=11)
+    packed = np.frombuffer(synth.pack_pcm(pcm, bps), dtype=np.uint8)
+    a = api.encode_batch(gpu_lib, pcm, 48000, bps, 8)
+    b = api.encode_batch(gpu_lib, packed, 48000, bps, 8, pcm_format=fmt,
+                         nsamples=pcm.shape[0], channels=2)
+    assert a.payload == b.payload and a.streaminfo == b.streaminfo
+
+
+def test_matches_compiled_reference(gpu_lib, oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    ref = oracle.ref_library()
+    for level, ch, bps, rate in [(5, 2, 16, 44100), (8, 2, 16, 44100), (12, 2, 24, 96000)]:
+        pcm = synth.synth_pcm(8192 * 2 + 2048, ch, bps, rate, seed=level)
+        want = api.encode_per_block(ref, pcm, rate, bps, level)
+        got = api.encode_batch(gpu_lib, pcm, rate, bps, level)
+        assert got.file_bytes() == want.file_bytes()

@@ -106,42 +106,52 @@ def synth_device(nsamples: int, seed: int, device):
 # clocks sampler
 # --------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int):
-        self.samples, self.reasons = [], set()
-        self.max_mhz = None
-        self._stop = threading.Event()
-        self.index = index
-        self.th = threading.Thread(target=self._run, daemon=True)
+    """`nvidia-smi -lms 100` in the background during the timed regions (the profiling
+    recipe's clocks line); median SM clock and any throttle reason that was ever active."""
 
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
-            try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in r.stdout.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(float(f[0]))
-                    self.max_mhz = float(f[1])
-                    for nme, v in zip(names, f[2:6]):
-                        if v.lower().startswith("active"):
-                            self.reasons.add(nme)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
 
     def start(self):
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
-        self.th.join(timeout=6)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        mhz, mx, reasons, watts = [], None, set(), []
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mhz.append(float(f[0])); mx = float(f[1]); watts.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(self.NAMES, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(mhz),
+                "power_w_max": max(watts) if watts else None}
 
 
 # --------------------------------------------------------------------------
@@ -290,7 +300,6 @@ def run_gpu_arm(args):
         device_pass()
         ev[i + 1].record(stream)
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[args.steps])
     stages = enc.stage_times()
@@ -340,6 +349,7 @@ def run_gpu_arm(args):
             e2e_bytes, h2d, d2h = int(rc), int(st.h2d_bytes), int(st.d2h_bytes)
             md5_hex = bytes(si.md5sum).hex()
     enc2.close()
+    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -427,7 +437,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

@@ -42,6 +42,17 @@ CASES = [
     ("l8_2level", 4096 * 2, 2, 16, 44100, "mix", 8, {"order_method": 2}),
     ("l8_8level", 4096 * 2, 2, 16, 44100, "mix", 8, {"order_method": 4}),
     ("l9_novbs", 4096 * 3, 2, 16, 44100, "mix", 9, {"variable_block_size": 0}),
+    # maximum block sizes: blocks that do not fit shared memory take the global-memory paths
+    ("bs65535_8ch_s24", 65535 + 4000, 8, 24, 48000, "mix", 8, {"block_size": 65535}),
+    ("bs65535_mono", 65535 * 2, 1, 16, 44100, "mix", 5, {"block_size": 65535}),
+    ("bs32768_l8", 32768 * 2 + 10, 2, 16, 44100, "mix", 8, {"block_size": 32768}),
+    ("bs32768_l12_vbs", 32768 * 2, 2, 24, 96000, "impulses", 12, {"block_size": 32768}),
+    ("bs16_min", 16 * 40 + 5, 2, 16, 44100, "mix", 5, {"block_size": 16}),
+    ("bs128_vbs", 128 * 20, 2, 16, 44100, "impulses", 9, {"block_size": 128}),
+    ("l5_7ch_20bit", 4096 * 2 + 50, 7, 20, 48000, "mix", 5, {}),
+    ("l8_pmin3", 4096 * 2, 2, 16, 44100, "mix", 8, {"min_partition_order": 3}),
+    ("l8_order32_log", 4096 * 2, 2, 16, 44100, "mix", 8, {"max_prediction_order": 32}),
+    ("l5_odd_block", 4095 * 2, 2, 16, 44100, "mix", 2, {"block_size": 4095}),
 ]
 
 

@@ -124,7 +124,7 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
 
     /* shared-memory staging where a whole block fits */
     e->lpc_smem_doubles = ((size_t)(B + 1) * 8 <= FB_SMEM_BUDGET) ? B + 1 : 0;
-    e->search_smem_ints = ((size_t)B * 4 <= FB_SMEM_BUDGET) ? B : 0;
+    e->search_smem_ints = ((size_t)fb_skew_words(B) * 4 <= FB_SMEM_BUDGET) ? fb_skew_words(B) : 0;
     {
         const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
         const uint64_t capw = (capb + 3u) >> 2;
@@ -133,7 +133,8 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     if (cfg->prediction_type == 2 && !e->lpc_smem_doubles)
         FB_TRY_ALLOC(e->d_win, sizeof(double) * (nint + e->max_subs + 16));
     cudaFuncSetAttribute(k_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, e->lpc_smem_doubles * 8);
-    cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
+    cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
+    cudaFuncSetAttribute(k_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
     cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, e->pack_smem_words * 4);
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { set_err(err, errlen, "cudaFuncSetAttribute failed", ce); fb_engine_destroy(e); return nullptr; }
@@ -206,15 +207,22 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     e->launches += 1;
     FB_MARK(2);
     if (cfg.prediction_type == 2) {
-        FB_LAUNCH(k_lpc, dim3(grid_subs), dim3(FB_LPC_THREADS), (size_t)e->lpc_smem_doubles * 8, st,
+        const int lpc_threads = 32 * ((2 * (cfg.max_order + 1) + 31) / 32);
+        FB_LAUNCH(k_lpc, dim3(grid_subs), dim3(lpc_threads), (size_t)e->lpc_smem_doubles * 8, st,
                   cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts,
                   e->d_win, e->lpc_smem_doubles);
         e->launches += 1;
     }
     FB_MARK(3);
-    FB_LAUNCH(k_search, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
-              cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_coefs, e->d_shifts,
-              e->search_smem_ints);
+    if (cfg.prediction_type == 2 && cfg.max_order > 12) {
+        FB_LAUNCH(k_search<32>, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
+                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_coefs, e->d_shifts,
+                  e->search_smem_ints);
+    } else {
+        FB_LAUNCH(k_search<12>, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
+                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_coefs, e->d_shifts,
+                  e->search_smem_ints);
+    }
     FB_MARK(4);
     FB_LAUNCH(k_pack, dim3(grid_frames), dim3(FB_PACK_THREADS), (size_t)e->pack_smem_words * 4, st,
               cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,

@@ -15,7 +15,7 @@
 
 #include "dev_common.cuh"
 
-#define FB_LPC_THREADS 64
+#define FB_LPC_THREADS 96      /* launch bound; actual block = 32 * ceil(2*(lag+1)/32) */
 #define FB_MAX_ORDER 32
 
 /* x86-64 cvttsd2si semantics of the reference's `int q = double` */
@@ -115,10 +115,74 @@ __device__ void fb_quantize(double *in, int order, int32_t *out, int32_t *shift)
     *shift = sh;
 }
 
+/* window (lpc.c:28-40) + the autocorrelation chains (lpc.c:57-68) on a window buffer
+ * whose address space the caller fixes (shared for blocks that fit, global otherwise),
+ * so that the shared variant compiles to LDS/STS. */
+__device__ __forceinline__ void fb_window_autocorr(const int32_t *__restrict__ x, double *w, int n,
+                                                   int lag, double *s_autoc)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    /* odd n: the centre sample is uninitialised in the reference; defined as 0.0 here
+     * (parity-exempt) */
+    {
+        const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
+        const int half = n >> 1;
+        for (int i = tid; i < half; i += T) {
+            const double d = __dsub_rn(cc, (double)i);
+            const double win = __dsub_rn(1.0, __dmul_rn(d, d));
+            w[i] = __dmul_rn((double)x[i], win);
+            w[n - 1 - i] = __dmul_rn((double)x[n - 1 - i], win);
+        }
+        if (tid == 0) {
+            if (n & 1) w[half] = 0.0;
+            w[n] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    /* chain (i, 0) = `temp`, (i, 1) = `temp2` of lpc.c:57-68.  The products do not depend
+     * on the running sum, so loads and multiplies of the next 8 terms are issued while the
+     * strictly ordered add chain of the current 8 drains. */
+    for (int ch = tid; ch < 2 * (lag + 1); ch += T) {
+        const int i = ch >> 1, a = ch & 1;
+        double s = 1.0;
+        if (a == 0)
+            for (int j = 0; j <= lag - i; j++)
+                s = __dadd_rn(s, __dmul_rn(w[j + i], w[j]));
+        int j = lag + 1 + a;
+        const int last = n - 1;
+        if (j + 14 <= last) {
+            double u0[8], v0[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { u0[q] = w[j + 2 * q]; v0[q] = w[j + 2 * q - i]; }
+            while (j + 30 <= last) {
+                double u1[8], v1[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { u1[q] = w[j + 16 + 2 * q]; v1[q] = w[j + 16 + 2 * q - i]; }
+                double p[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) p[q] = __dmul_rn(u0[q], v0[q]);
+#pragma unroll
+                for (int q = 0; q < 8; q++) s = __dadd_rn(s, p[q]);
+#pragma unroll
+                for (int q = 0; q < 8; q++) { u0[q] = u1[q]; v0[q] = v1[q]; }
+                j += 16;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) s = __dadd_rn(s, __dmul_rn(u0[q], v0[q]));
+            j += 16;
+        }
+        for (; j <= last; j += 2)
+            s = __dadd_rn(s, __dmul_rn(w[j], w[j - i]));
+        s_autoc[ch] = s;
+    }
+}
+
 /*
  * coefs_out: [subframe][32][32] int32, shift_out: [subframe][32].
  * win_g: global window scratch (n+1 doubles per subframe at offset
  * start*C + c*n + subframe) used only when the block does not fit shared memory.
+ * Block = 32 * ceil(2*(lag+1)/32) threads: one warp per subframe up to order 15.
  */
 __global__ void __launch_bounds__(FB_LPC_THREADS)
 k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
@@ -142,40 +206,12 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
     if (sb->is_const || n < 5 || cfg.prediction_type != 2 || n <= lag) return;
 
     const int32_t *x = smp + (size_t)fr.start * C + (size_t)c * n;
-    double *w = (n + 1 <= smem_doubles) ? (double *)dyn
-                                        : win_g + ((size_t)fr.start * C + (size_t)c * n + sf);
     const int tid = threadIdx.x, T = blockDim.x;
 
-    /* window, lpc.c:28-40 (odd n: centre sample is uninitialised in the
-     * reference; defined as 0.0 here, parity-exempt) */
-    {
-        const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
-        const int half = n >> 1;
-        for (int i = tid; i < half; i += T) {
-            const double d = __dsub_rn(cc, (double)i);
-            const double win = __dsub_rn(1.0, __dmul_rn(d, d));
-            w[i] = __dmul_rn((double)x[i], win);
-            w[n - 1 - i] = __dmul_rn((double)x[n - 1 - i], win);
-        }
-        if (tid == 0) {
-            if (n & 1) w[half] = 0.0;
-            w[n] = 0.0;
-        }
-    }
-    __syncthreads();
-
-    /* autocorrelation chains, lpc.c:57-68: chain (i, 0) = `temp`, (i, 1) = `temp2` */
-    for (int ch = tid; ch < 2 * (lag + 1); ch += T) {
-        const int i = ch >> 1, a = ch & 1;
-        double s = 1.0;
-        if (a == 0)
-            for (int j = 0; j <= lag - i; j++)
-                s = __dadd_rn(s, __dmul_rn(w[j + i], w[j]));
-        /* j = lag+1, lag+3, ...; chain a handles element j+a */
-        for (int j = lag + 1 + a; j <= n - 1; j += 2)
-            s = __dadd_rn(s, __dmul_rn(w[j], w[j - i]));
-        s_autoc[ch] = s;
-    }
+    if (n + 1 <= smem_doubles)
+        fb_window_autocorr(x, reinterpret_cast<double *>(dyn), n, lag, s_autoc);
+    else
+        fb_window_autocorr(x, win_g + ((size_t)fr.start * C + (size_t)c * n + sf), n, lag, s_autoc);
     __syncthreads();
     /* fold the two accumulators (autoc[i] = temp + temp2) in place */
     if (tid == 0)

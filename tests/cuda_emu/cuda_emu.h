@@ -33,6 +33,15 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 
+struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(8))) int2 { int x, y; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
+inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 v = {x, y}; return v; }
+
 namespace cuemu {
 
 struct Fiber {

@@ -124,7 +124,7 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
 
     /* shared-memory staging where a whole block fits */
     e->lpc_smem_doubles = ((size_t)(B + 1) * 8 <= FB_SMEM_BUDGET) ? B + 1 : 0;
-    e->search_smem_ints = ((size_t)fb_skew_words(B) * 4 <= FB_SMEM_BUDGET) ? fb_skew_words(B) : 0;
+    e->search_smem_ints = ((size_t)fb_search_smem_words(B) * 4 <= FB_SMEM_BUDGET) ? fb_search_smem_words(B) : 0;
     {
         const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
         const uint64_t capw = (capb + 3u) >> 2;

@@ -178,7 +178,9 @@ __device__ uint32_t fb_evaluate(FbSearchShared &S, const int32_t *x, int n, int 
  * 16-sample run is followed by 4 pad words so that 128-bit loads of threads
  * whose runs are 16 samples apart hit distinct bank groups */
 __host__ __device__ __forceinline__ int fb_skew(int logical) { return logical + ((logical >> 4) << 2); }
-__host__ __device__ __forceinline__ int fb_skew_words(int n) { return fb_skew(n + FB_HIST + FB_RUN) + 8; }
+__host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n + FB_HIST + FB_RUN) + 8 + 1) & ~1; }
+/* staged plane + one 64-bit zig-zag sum per 16-sample run, in 32-bit words */
+__host__ __device__ __forceinline__ int fb_search_smem_words(int n) { return fb_skew_words(n) + 2 * (((n + FB_RUN - 1) / FB_RUN) + 2); }
 
 /*
  * Residual of the samples [i0, i0+16) with a register sliding window.
@@ -189,7 +191,7 @@ __host__ __device__ __forceinline__ int fb_skew_words(int n) { return fb_skew(n 
 template <int P, bool WIDE>
 __device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t *xs, int n, int order,
                                                 int psize, int nparts, int tile_base,
-                                                int32_t *res_out)
+                                                int32_t *res_out, unsigned long long *runsum)
 {
     const int tid = threadIdx.x;
     const int i0 = tile_base + tid * FB_RUN;
@@ -236,23 +238,33 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t
         }
     }
 
-    /* zig-zag sums into the finest partition level (rice.c:76-95) */
-    const int p0 = i0 / psize;
-    if (i0 >= order && i0 + FB_RUN <= n && (i0 - p0 * psize) + FB_RUN <= psize) {
-        /* common case: the whole run lies in one partition */
-        if (WIDE) {
-            unsigned long long acc = 0;
+    /* zig-zag sums (rice.c:76-95).  Partitions that are whole multiples of the run length
+     * (the rule for every power-of-two block size): one sum per run, folded into the
+     * partition sums after the tiles -- no atomics on the hot loop. */
+    if (runsum) {
+        unsigned long long acc;
+        if (i0 >= order && i0 + FB_RUN <= n) {
+            if (WIDE) {
+                acc = 0;
 #pragma unroll
-            for (int k = 0; k < FB_RUN; k++) acc += fb_zigzag(r[k]);
-            if (acc) atomicAdd(&S.sums[nparts - 1 + p0], acc);
+                for (int k = 0; k < FB_RUN; k++) acc += fb_zigzag(r[k]);
+            } else {
+                uint32_t a32 = 0;
+#pragma unroll
+                for (int k = 0; k < FB_RUN; k++) a32 += fb_zigzag(r[k]);
+                acc = a32;
+            }
         } else {
-            uint32_t acc = 0;
+            acc = 0;
 #pragma unroll
-            for (int k = 0; k < FB_RUN; k++) acc += fb_zigzag(r[k]);
-            if (acc) atomicAdd(&S.sums[nparts - 1 + p0], (unsigned long long)acc);
+            for (int k = 0; k < FB_RUN; k++)
+                if (i0 + k >= order && i0 + k < n) acc += fb_zigzag(r[k]);
         }
-    } else {
-        /* warm-up, block tail, or a partition boundary inside the run */
+        runsum[i0 >> 4] = acc;
+        return;
+    }
+    /* general partition sizes: walk the run, flushing at partition boundaries */
+    {
         const int istart = i0 < order ? order : i0;
         int pcur = istart / psize;
         int nb = (pcur + 1) * psize;
@@ -277,10 +289,10 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t
 
 template <int P, bool WIDE>
 __device__ __noinline__ void fb_tiles(FbSearchShared &S, const int32_t *xs, int n, int order, int psize,
-                                      int nparts, int32_t *res_out)
+                                      int nparts, int32_t *res_out, unsigned long long *runsum)
 {
     for (int tile = 0; tile < n; tile += (int)blockDim.x * FB_RUN)
-        fb_run_residual<P, WIDE>(S, xs, n, order, psize, nparts, tile, res_out);
+        fb_run_residual<P, WIDE>(S, xs, n, order, psize, nparts, tile, res_out, runsum);
 }
 
 /*
@@ -305,10 +317,13 @@ __device__ uint32_t fb_evaluate_fast(FbSearchShared &S, const int32_t *xs, int n
     const bool narrow = pm < 0x80000000ull &&
                         ((unsigned long long)maxabs + (pm >> S.shift) + 1ull) < (1ull << 26);
     const int P = (order + 3) & ~3;
+    /* per-run sums are usable when every partition is a whole number of runs */
+    unsigned long long *runsum = (psize % FB_RUN) == 0
+        ? reinterpret_cast<unsigned long long *>(const_cast<int32_t *>(xs) + fb_skew_words(n)) : nullptr;
 #define FB_CASE(PP)                                                                           \
     case PP:                                                                                  \
-        if (narrow) fb_tiles<PP, false>(S, xs, n, order, psize, nparts, res_out);             \
-        else        fb_tiles<PP, true>(S, xs, n, order, psize, nparts, res_out);              \
+        if (narrow) fb_tiles<PP, false>(S, xs, n, order, psize, nparts, res_out, runsum);             \
+        else        fb_tiles<PP, true>(S, xs, n, order, psize, nparts, res_out, runsum);              \
         break;
     switch (P) {
         case 0:
@@ -318,14 +333,23 @@ __device__ uint32_t fb_evaluate_fast(FbSearchShared &S, const int32_t *xs, int n
                 switch (P) {
                     FB_CASE(16) FB_CASE(20) FB_CASE(24) FB_CASE(28)
                     default:
-                        if (narrow) fb_tiles<32, false>(S, xs, n, order, psize, nparts, res_out);
-                        else        fb_tiles<32, true>(S, xs, n, order, psize, nparts, res_out);
+                        if (narrow) fb_tiles<32, false>(S, xs, n, order, psize, nparts, res_out, runsum);
+                        else        fb_tiles<32, true>(S, xs, n, order, psize, nparts, res_out, runsum);
                         break;
                 }
             }
             break;
     }
 #undef FB_CASE
+    if (runsum) {
+        __syncthreads();
+        const int per = psize / FB_RUN;
+        for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
+            unsigned long long sum = 0;
+            for (int q = 0; q < per; q++) sum += runsum[p * per + q];
+            S.sums[nparts - 1 + p] = sum;
+        }
+    }
     return fb_eval_finish(S, n, is_lpc, order, obits, pmin, pmax, store);
 }
 
@@ -369,7 +393,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     }
 
     /* stage the plane: skewed layout, FB_HIST zero samples in front (fast path) */
-    const bool fast = fb_skew_words(n) <= smem_ints;
+    const bool fast = fb_search_smem_words(n) <= smem_ints;
     int32_t *xs = (int32_t *)dyn;
     if (fast) {
         for (int L = tid; L < FB_HIST; L += T) xs[fb_skew(L)] = 0;

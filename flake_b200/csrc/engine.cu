@@ -123,15 +123,13 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     }
 
     /* shared-memory staging where a whole block fits */
-    e->lpc_smem_doubles = ((size_t)(B + 1) * 8 <= FB_SMEM_BUDGET) ? B + 1 : 0;
+    e->lpc_smem_doubles = FB_LPC_RING + cfg->max_order * FB_MAX_ORDER;   /* ring + lpc[lag][32] */
     e->search_smem_ints = ((size_t)fb_search_smem_words(B) * 4 <= FB_SMEM_BUDGET) ? fb_search_smem_words(B) : 0;
     {
         const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
         const uint64_t capw = (capb + 3u) >> 2;
         e->pack_smem_words = (capw * 4u <= FB_SMEM_BUDGET) ? (int)capw : 0;
     }
-    if (cfg->prediction_type == 2 && !e->lpc_smem_doubles)
-        FB_TRY_ALLOC(e->d_win, sizeof(double) * (nint + e->max_subs + 16));
     cudaFuncSetAttribute(k_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, e->lpc_smem_doubles * 8);
     cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
     cudaFuncSetAttribute(k_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
@@ -209,8 +207,7 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     if (cfg.prediction_type == 2) {
         const int lpc_threads = 32 * ((2 * (cfg.max_order + 1) + 31) / 32);
         FB_LAUNCH(k_lpc, dim3(grid_subs), dim3(lpc_threads), (size_t)e->lpc_smem_doubles * 8, st,
-                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts,
-                  e->d_win, e->lpc_smem_doubles);
+                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts);
         e->launches += 1;
     }
     FB_MARK(3);

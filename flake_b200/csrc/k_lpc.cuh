@@ -115,83 +115,43 @@ __device__ void fb_quantize(double *in, int order, int32_t *out, int32_t *shift)
     *shift = sh;
 }
 
-/* window (lpc.c:28-40) + the autocorrelation chains (lpc.c:57-68) on a window buffer
- * whose address space the caller fixes (shared for blocks that fit, global otherwise),
- * so that the shared variant compiles to LDS/STS. */
-__device__ __forceinline__ void fb_window_autocorr(const int32_t *__restrict__ x, double *w, int n,
-                                                   int lag, double *s_autoc)
-{
-    const int tid = threadIdx.x, T = blockDim.x;
-    /* odd n: the centre sample is uninitialised in the reference; defined as 0.0 here
-     * (parity-exempt) */
-    {
-        const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
-        const int half = n >> 1;
-        for (int i = tid; i < half; i += T) {
-            const double d = __dsub_rn(cc, (double)i);
-            const double win = __dsub_rn(1.0, __dmul_rn(d, d));
-            w[i] = __dmul_rn((double)x[i], win);
-            w[n - 1 - i] = __dmul_rn((double)x[n - 1 - i], win);
-        }
-        if (tid == 0) {
-            if (n & 1) w[half] = 0.0;
-            w[n] = 0.0;
-        }
-    }
-    __syncthreads();
+#define FB_LPC_CHUNK 512          /* window samples produced per round */
+#define FB_LPC_HIST  32           /* samples of the previous round kept in front (>= max lag) */
+#define FB_LPC_BUF   (FB_LPC_HIST + FB_LPC_CHUNK)
+#define FB_LPC_RING  (2 * FB_LPC_BUF)   /* two buffers, alternating */
 
-    /* chain (i, 0) = `temp`, (i, 1) = `temp2` of lpc.c:57-68.  The products do not depend
-     * on the running sum, so loads and multiplies of the next 8 terms are issued while the
-     * strictly ordered add chain of the current 8 drains. */
-    for (int ch = tid; ch < 2 * (lag + 1); ch += T) {
-        const int i = ch >> 1, a = ch & 1;
-        double s = 1.0;
-        if (a == 0)
-            for (int j = 0; j <= lag - i; j++)
-                s = __dadd_rn(s, __dmul_rn(w[j + i], w[j]));
-        int j = lag + 1 + a;
-        const int last = n - 1;
-        if (j + 14 <= last) {
-            double u0[8], v0[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) { u0[q] = w[j + 2 * q]; v0[q] = w[j + 2 * q - i]; }
-            while (j + 30 <= last) {
-                double u1[8], v1[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) { u1[q] = w[j + 16 + 2 * q]; v1[q] = w[j + 16 + 2 * q - i]; }
-                double p[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) p[q] = __dmul_rn(u0[q], v0[q]);
-#pragma unroll
-                for (int q = 0; q < 8; q++) s = __dadd_rn(s, p[q]);
-#pragma unroll
-                for (int q = 0; q < 8; q++) { u0[q] = u1[q]; v0[q] = v1[q]; }
-                j += 16;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) s = __dadd_rn(s, __dmul_rn(u0[q], v0[q]));
-            j += 16;
-        }
-        for (; j <= last; j += 2)
-            s = __dadd_rn(s, __dmul_rn(w[j], w[j - i]));
-        s_autoc[ch] = s;
-    }
+/* data1[p] of lpc.c:46-56: windowed sample p, 0 at p == n.  The window value depends
+ * only on min(p, n-1-p) (lpc.c:33-39), so it is recomputed per position instead of being
+ * kept for the mirrored sample.  Odd n: the centre sample is uninitialised in the
+ * reference; defined as 0.0 here (parity-exempt). */
+__device__ __forceinline__ double fb_windowed(const int32_t *__restrict__ x, int p, int n, int half, double cc)
+{
+    if (p >= n || ((n & 1) && p == half)) return 0.0;
+    const int i = p < half ? p : n - 1 - p;
+    const double d = __dsub_rn(cc, (double)i);
+    const double win = __dsub_rn(1.0, __dmul_rn(d, d));
+    return __dmul_rn((double)x[p], win);
 }
 
 /*
  * coefs_out: [subframe][32][32] int32, shift_out: [subframe][32].
- * win_g: global window scratch (n+1 doubles per subframe at offset
- * start*C + c*n + subframe) used only when the block does not fit shared memory.
- * Block = 32 * ceil(2*(lag+1)/32) threads: one warp per subframe up to order 15.
+ * Block = 32 * ceil(2*(lag+1)/32) threads: thread ch owns chain (lag ch>>1, accumulator ch&1)
+ * of lpc.c:57-68 -- one warp per subframe up to order 15.
+ *
+ * The chains of all lags advance in lockstep over the sample index, so only a sliding
+ * window of the windowed signal is live: it is produced 512 samples at a time into a
+ * 1024-entry shared ring (8 KB) straight from the int32 plane, whatever the block size.
+ * Dynamic shared memory: ring[1024] doubles, then lpc[lag][32] doubles.
  */
 __global__ void __launch_bounds__(FB_LPC_THREADS)
 k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
-      FbSub *subs, int32_t *coefs_out, int32_t *shift_out, double *win_g, int smem_doubles)
+      FbSub *subs, int32_t *coefs_out, int32_t *shift_out)
 {
     FB_DYN_SMEM(dyn);
     __shared__ double s_autoc[2 * (FB_MAX_ORDER + 1)];
-    __shared__ double s_lpc[FB_MAX_ORDER][FB_MAX_ORDER];
     __shared__ int s_est;
+    double *ring = reinterpret_cast<double *>(dyn);
+    double (*s_lpc)[FB_MAX_ORDER] = reinterpret_cast<double (*)[FB_MAX_ORDER]>(ring + FB_LPC_RING);
 
     const int C = cfg.channels;
     const uint32_t sf = blockIdx.x;
@@ -205,13 +165,83 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
     /* same gate as optimize.c:143-193: only the LPC branch needs coefficients */
     if (sb->is_const || n < 5 || cfg.prediction_type != 2 || n <= lag) return;
 
-    const int32_t *x = smp + (size_t)fr.start * C + (size_t)c * n;
+    const int32_t *__restrict__ x = smp + (size_t)fr.start * C + (size_t)c * n;
     const int tid = threadIdx.x, T = blockDim.x;
+    const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
+    const int half = n >> 1;
 
-    if (n + 1 <= smem_doubles)
-        fb_window_autocorr(x, reinterpret_cast<double *>(dyn), n, lag, s_autoc);
-    else
-        fb_window_autocorr(x, win_g + ((size_t)fr.start * C + (size_t)c * n + sf), n, lag, s_autoc);
+    /* chain state */
+    const bool active = tid < 2 * (lag + 1);
+    const int ci = tid >> 1, ca = tid & 1;
+    double s = 1.0;                               /* lpc.c:58-59: both accumulators start at 1.0 */
+    int j = lag + 1 + ca;                         /* next tail term of this chain */
+    const int last = n - 1;
+
+    int which = 0;
+    for (int base = 0; base <= n; base += FB_LPC_CHUNK, which ^= 1) {
+        double *buf = ring + which * FB_LPC_BUF;              /* buf[FB_LPC_HIST + (p - base)] = data1[p] */
+        const double *prev = ring + (which ^ 1) * FB_LPC_BUF;
+        const int end = min(base + FB_LPC_CHUNK, n + 1);      /* positions [base, end) */
+        /* produce: plane loads first (independent), then the FP64 window arithmetic */
+        for (int p0 = base + tid; p0 < end; p0 += 8 * T) {
+            int32_t xv[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int p = p0 + q * T; xv[q] = p < n ? x[p] : 0; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int p = p0 + q * T;
+                if (p < end) {
+                    double v = 0.0;
+                    if (p < n && !((n & 1) && p == half)) {
+                        const int i = p < half ? p : n - 1 - p;
+                        const double d = __dsub_rn(cc, (double)i);
+                        v = __dmul_rn((double)xv[q], __dsub_rn(1.0, __dmul_rn(d, d)));
+                    }
+                    buf[FB_LPC_HIST + (p - base)] = v;
+                }
+            }
+        }
+        if (tid < FB_LPC_HIST)                                  /* carry the last 32 samples over */
+            buf[tid] = base ? prev[FB_LPC_CHUNK + tid] : 0.0;
+        __syncthreads();
+        if (active) {
+            const double *w = buf + FB_LPC_HIST - base;          /* w[p] = data1[p], p >= base - 32 */
+            if (base == 0 && ca == 0)                            /* head terms, lpc.c:60-61 */
+                for (int q = 0; q <= lag - ci; q++)
+                    s = __dadd_rn(s, __dmul_rn(w[q + ci], w[q]));
+            const int lim = min(end - 1, last);
+            /* tail terms in order; the products do not depend on the running sum, so the
+             * loads and multiplies of the next 8 terms are issued while the strictly
+             * ordered add chain of the current 8 drains */
+            if (j + 14 <= lim) {
+                const double *pu = w + j, *pv = w + j - ci;
+                double u0[8], v0[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { u0[q] = pu[2 * q]; v0[q] = pv[2 * q]; }
+                while (j + 30 <= lim) {
+                    pu += 16; pv += 16;
+                    double u1[8], v1[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { u1[q] = pu[2 * q]; v1[q] = pv[2 * q]; }
+                    double pr[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) pr[q] = __dmul_rn(u0[q], v0[q]);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) s = __dadd_rn(s, pr[q]);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { u0[q] = u1[q]; v0[q] = v1[q]; }
+                    j += 16;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) s = __dadd_rn(s, __dmul_rn(u0[q], v0[q]));
+                j += 16;
+            }
+            for (; j <= lim; j += 2)
+                s = __dadd_rn(s, __dmul_rn(w[j], w[j - ci]));
+        }
+        __syncthreads();
+    }
+    if (active) s_autoc[tid] = s;
     __syncthreads();
     /* fold the two accumulators (autoc[i] = temp + temp2) in place */
     if (tid == 0)

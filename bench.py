@@ -190,21 +190,42 @@ def cpu_encode_threads(pcm_i32: np.ndarray, threads: int, steps: int, warmup: in
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation on this box's host cores.
+
+    The workload of the GPU arm is one 1-hour stream per rank.  libflake is single threaded
+    and its API is serial per stream (frame numbers and the MD5 chain through every block), so
+    the most host threads the reference can use on this workload is one per stream:
+    `--gpus N` streams -> N threads, one FlakeContext each.  Each step encodes a bounded sample
+    (the first ~66 s of audio) of every stream.  For orientation the line also carries
+    `all_cores`: every host core busy, each on its own independent stream segment -- more
+    streams than the workload has, i.e. what a corpus of many files would reach.
+    """
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     from flake_b200 import synth
     cores = os.cpu_count() or 1
-    threads = env_int("FLAKE_BENCH_REF_THREADS", cores)
-    per_thread = env_int("FLAKE_BENCH_REF_SAMPLES_PER_THREAD", BLOCK * 700)   # ~2.9 M samples, ~0.6 s of CPU
-    base = synth.synth_pcm(min(per_thread * threads, BLOCK * 700 * 4), CHANNELS, BPS, RATE, seed=0)
-    reps = (per_thread * threads + base.shape[0] - 1) // base.shape[0]
-    pcm = np.ascontiguousarray(np.tile(base, (reps, 1))[:per_thread * threads])
+    streams = max(1, min(args.gpus, cores))
+    threads = env_int("FLAKE_BENCH_REF_THREADS", streams)
+    per_thread = env_int("FLAKE_BENCH_REF_SAMPLES_PER_THREAD", BLOCK * 2800)   # 11.5 M samples, ~1 s of CPU
+    base = synth.synth_pcm(BLOCK * 700, CHANNELS, BPS, RATE, seed=0)
+
+    def tiled(total):
+        reps = (total + base.shape[0] - 1) // base.shape[0]
+        return np.ascontiguousarray(np.tile(base, (reps, 1))[:total])
+
+    pcm = tiled(per_thread * threads)
     total, times, kind = cpu_encode_threads(pcm, threads, args.steps, max(1, min(args.warmup, 1)))
     ms = 1e3 * float(np.mean(times))
     val = total / (ms * 1e-3) / 1e6
-    sample = "%d threads x %d samples (%.0f s of audio each) of the C2 signal per step" % (
+    sample = "%d stream(s) x first %d samples (%.0f s of audio) per step, one thread per stream" % (
         threads, total // threads, total / threads / RATE)
+    allc = None
+    if cores > threads and not os.environ.get("FLAKE_BENCH_SKIP_ALL_CORES"):
+        seg = BLOCK * 700
+        t2, times2, _ = cpu_encode_threads(tiled(seg * cores), cores, 1, 1)
+        allc = {"value": round(t2 / times2[0] / 1e6, 3), "unit": "MSamples/s", "cores": cores,
+                "sample": "%d independent stream segments of %d samples" % (cores, seg)}
     line = {
         "impl": "reference", "metric": "MSamples/s encoded, flake -8", "value": round(val, 3),
         "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -212,9 +233,10 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": round(val, 3), "unit": "MSamples/s", "cores": threads, "kind": kind,
-                         "sample": sample},
+                         "sample": sample, "host_cores_available": cores},
         "e2e": {"value": round(val, 3), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "audio_seconds_per_s": round(val * 1e6 / RATE, 1),
+        "all_cores": allc,
     }
     print(json.dumps(line), flush=True)
 

@@ -29,6 +29,8 @@
 
 typedef struct FbLane {
     void *h_in, *d_in;              /* pinned staging + device copy of the chunk's PCM */
+    void *h_pack;                   /* pinned: the chunk packed at ceil(bps/8) bytes (digest layout) */
+    size_t pack_bytes;              /* bytes of h_pack in use */
     void *d_out, *h_out;            /* compacted frames */
     uint32_t *d_flen, *d_fbs, *h_flen, *h_fbs;
     FbSummary *d_sum, *h_sum;
@@ -294,7 +296,7 @@ static int write_stream_header(FbCtx *c, unsigned char *h)
 /* ------------------------------------------------------------------ */
 static void lane_free(FbLane *l)
 {
-    fb_cuda_free_host(l->h_in); fb_cuda_free(l->d_in); fb_cuda_free(l->d_out);
+    fb_cuda_free_host(l->h_in); fb_cuda_free_host(l->h_pack); fb_cuda_free(l->d_in); fb_cuda_free(l->d_out);
     fb_cuda_free_host(l->h_out);
     fb_cuda_free(l->d_flen); fb_cuda_free(l->d_fbs); fb_cuda_free(l->d_sum);
     fb_cuda_free_host(l->h_flen); fb_cuda_free_host(l->h_fbs); fb_cuda_free_host(l->h_sum);
@@ -311,6 +313,7 @@ static int lane_alloc(FbLane *l, const FbEngine *e, const FbConfig *cfg, void *h
     const uint32_t mf = fb_engine_max_frames(e);
     memset(l, 0, sizeof *l);
     l->h_in = fb_cuda_malloc_host(in_bytes);
+    l->h_pack = fb_cuda_malloc_host(in_bytes / 4u * (uint64_t)((cfg->bps + 7) >> 3) + 64u);
     l->d_in = fb_cuda_malloc(in_bytes);
     l->d_out = fb_cuda_malloc(out_bytes);
     l->h_out = h_out_external ? NULL : fb_cuda_malloc_host(out_bytes);
@@ -321,7 +324,7 @@ static int lane_alloc(FbLane *l, const FbEngine *e, const FbConfig *cfg, void *h
     l->h_fbs = (uint32_t *)fb_cuda_malloc_host(sizeof(uint32_t) * mf);
     l->h_sum = (FbSummary *)fb_cuda_malloc_host(sizeof(FbSummary));
     l->ev_done = fb_cuda_event_create();
-    if (!l->h_in || !l->d_in || !l->d_out || (!l->h_out && !h_out_external) || !l->d_flen ||
+    if (!l->h_in || !l->h_pack || !l->d_in || !l->d_out || (!l->h_out && !h_out_external) || !l->d_flen ||
         !l->d_fbs || !l->d_sum || !l->h_flen || !l->h_fbs || !l->h_sum || !l->ev_done) {
         lane_free(l);
         return -1;
@@ -339,17 +342,71 @@ static size_t pcm_bytes_per_sample(int fmt)
     }
 }
 
-/* stage + upload + enqueue the engine pass + fetch the summary (all async) */
-static int lane_submit(FbCtx *c, FbEngine *e, FbLane *l, const void *pcm, int fmt,
-                       uint64_t nsamples, uint32_t first_number)
+/*
+ * int32 samples -> the digest layout of md5.c:281-320 (little-endian, ceil(bps/8) bytes,
+ * low bytes of each sample) in one pass.  Returns 1 when every sample is representable
+ * in that many bytes, i.e. the packed buffer can also feed the GPU (sign extension on
+ * ingest reproduces the int32 exactly); 0 when some sample is out of range and the
+ * encoder must see the caller's int32 values untouched.
+ */
+static int pack_s32(const int32_t *src, size_t count, int bytes, uint8_t *dst)
 {
-    const size_t bytes = (size_t)nsamples * (size_t)c->channels * pcm_bytes_per_sample(fmt);
-    memcpy(l->h_in, pcm, bytes);
+    int32_t bad = 0;
+    if (bytes == 2) {
+        int16_t *d = (int16_t *)dst;
+        for (size_t i = 0; i < count; i++) { const int32_t v = src[i]; const int16_t t = (int16_t)v; d[i] = t; bad |= v ^ (int32_t)t; }
+    } else if (bytes == 3) {
+        for (size_t i = 0; i < count; i++) {
+            const int32_t v = src[i];
+            dst[3 * i] = (uint8_t)v; dst[3 * i + 1] = (uint8_t)(v >> 8); dst[3 * i + 2] = (uint8_t)(v >> 16);
+            bad |= v ^ ((v << 8) >> 8);
+        }
+    } else if (bytes == 1) {
+        int8_t *d = (int8_t *)dst;
+        for (size_t i = 0; i < count; i++) { const int32_t v = src[i]; const int8_t t = (int8_t)v; d[i] = t; bad |= v ^ (int32_t)t; }
+    } else {
+        memcpy(dst, src, count * 4);
+    }
+    return bad == 0;
+}
+
+static int packed_format(int bytes)
+{
+    return bytes == 2 ? FLAKE_B200_PCM_S16LE : bytes == 3 ? FLAKE_B200_PCM_S24LE
+         : bytes == 1 ? FLAKE_B200_PCM_S8 : FLAKE_B200_PCM_S32;
+}
+
+/* Host staging of one chunk.  int32 input is packed to the digest layout (which the MD5
+ * thread then hashes straight from the pinned buffer, and which is also what gets uploaded
+ * when it is lossless: half or three quarters of the PCIe bytes); packed input is copied. */
+static void lane_stage(FbCtx *c, FbLane *l, const void *pcm, int fmt, uint64_t nsamples,
+                       const void **upload, size_t *upload_bytes, int *upload_fmt)
+{
+    const size_t count = (size_t)nsamples * (size_t)c->channels;
     l->nsamples = nsamples;
-    if (fb_cuda_h2d(l->d_in, l->h_in, bytes, c->st)) return -3;
+    l->pack_bytes = 0;
+    if (fmt == FLAKE_B200_PCM_S32) {
+        const int bytes = (c->bps + 7) >> 3;
+        const int lossless = pack_s32((const int32_t *)pcm, count, bytes, (uint8_t *)l->h_pack);
+        l->pack_bytes = count * (size_t)bytes;
+        if (lossless) {
+            *upload = l->h_pack; *upload_bytes = l->pack_bytes; *upload_fmt = packed_format(bytes);
+            return;
+        }
+    }
+    const size_t bytes = count * pcm_bytes_per_sample(fmt);
+    memcpy(l->h_in, pcm, bytes);
+    *upload = l->h_in; *upload_bytes = bytes; *upload_fmt = fmt;
+}
+
+/* upload + enqueue the engine pass + fetch the summary (all async) */
+static int lane_launch(FbCtx *c, FbEngine *e, FbLane *l, const void *upload, size_t bytes, int fmt,
+                       uint32_t first_number)
+{
+    if (fb_cuda_h2d(l->d_in, upload, bytes, c->st)) return -3;
     c->stats.h2d_bytes += bytes;
     const uint64_t before = fb_engine_launch_count(e);
-    const int rc = fb_engine_encode_device(e, l->d_in, fmt, nsamples, first_number, l->d_out,
+    const int rc = fb_engine_encode_device(e, l->d_in, fmt, l->nsamples, first_number, l->d_out,
                                            l->d_flen, l->d_fbs, l->d_sum, c->st);
     if (rc) { snprintf(c->err, sizeof c->err, "%s", fb_engine_last_error(e)); return -3; }
     c->stats.kernel_launches += fb_engine_launch_count(e) - before;
@@ -357,6 +414,14 @@ static int lane_submit(FbCtx *c, FbEngine *e, FbLane *l, const void *pcm, int fm
     c->stats.d2h_bytes += sizeof(FbSummary);
     if (fb_cuda_event_record(l->ev_done, c->st)) return -3;
     return 0;
+}
+
+static int lane_submit(FbCtx *c, FbEngine *e, FbLane *l, const void *pcm, int fmt,
+                       uint64_t nsamples, uint32_t first_number)
+{
+    const void *up; size_t nb; int ufmt;
+    lane_stage(c, l, pcm, fmt, nsamples, &up, &nb, &ufmt);
+    return lane_launch(c, e, l, up, nb, ufmt, first_number);
 }
 
 /* wait for the pass, then pull frames + lengths (exact sizes) on the copy stream */
@@ -531,7 +596,7 @@ int flake_encode_frame(FlakeContext *s, const int *samples, int block_size)
         return -1;
     /* MD5 of this block while the GPU works (encode.c:1005-1006) */
     FbMd5 md5 = c->md5;
-    fb_md5_update_s32(&md5, (const int32_t *)samples, (size_t)block_size * (size_t)c->channels, c->bps);
+    fb_md5_update(&md5, c->one.h_pack, c->one.pack_bytes);     /* packed by lane_stage */
     if (lane_collect(c, &c->one, c->frame_buffer, c->frame_buffer_size, 0)) return -1;
     const FbSummary *sm = c->one.h_sum;
     if (sm->total_bytes == 0 || sm->total_bytes > 0x7fffffffull) return -1;
@@ -543,41 +608,45 @@ int flake_encode_frame(FlakeContext *s, const int *samples, int block_size)
 /* ------------------------------------------------------------------ */
 /* batch extension                                                      */
 /* ------------------------------------------------------------------ */
-typedef struct Md5Job {
+/*
+ * MD5 thread of a batch call.  Two sources:
+ *   direct  the caller's buffer already has the digest layout (packed input whose container
+ *           is ceil(bps/8) bytes): one fb_md5_update over it;
+ *   piped   int32 (or odd-container) input: the main thread packs each chunk into the lane's
+ *           pinned h_pack while staging it, this thread hashes chunk after chunk.  A lane is
+ *           re-used two chunks later, so the main thread waits for `consumed` before packing.
+ */
+typedef struct Md5Pipe {
     FbMd5 *md5;
-    const void *pcm;
-    int fmt, bps;
-    size_t count;                   /* individual samples (all channels) */
+    const void *direct; size_t direct_bytes;
+    pthread_mutex_t mu; pthread_cond_t cv;
+    uint64_t produced, consumed, total;
+    const void *ptr[2]; size_t len[2];
     double ms;
-} Md5Job;
+} Md5Pipe;
 
 static void *md5_worker(void *arg)
 {
-    Md5Job *j = (Md5Job *)arg;
-    const double t0 = now_ms();
-    const int want = (j->bps + 7) >> 3;
-    const size_t have = pcm_bytes_per_sample(j->fmt);
-    if (j->fmt != FLAKE_B200_PCM_S32 && have == (size_t)want) {
-        fb_md5_update(j->md5, j->pcm, j->count * have);       /* container == digest layout */
-    } else if (j->fmt == FLAKE_B200_PCM_S32) {
-        fb_md5_update_s32(j->md5, (const int32_t *)j->pcm, j->count, j->bps);
-    } else {
-        /* container wider/narrower than ceil(bps/8): widen, then repack */
-        int32_t tmp[4096];
-        const uint8_t *p = (const uint8_t *)j->pcm;
-        size_t left = j->count;
-        while (left) {
-            size_t take = left < 4096 ? left : 4096;
-            for (size_t i = 0; i < take; i++, p += have) {
-                if (have == 2) tmp[i] = (int16_t)(p[0] | (p[1] << 8));
-                else if (have == 3) tmp[i] = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)(int8_t)p[2] << 16));
-                else tmp[i] = (int8_t)p[0];
-            }
-            fb_md5_update_s32(j->md5, tmp, take, j->bps);
-            left -= take;
-        }
+    Md5Pipe *p = (Md5Pipe *)arg;
+    if (p->direct) {
+        const double t0 = now_ms();
+        fb_md5_update(p->md5, p->direct, p->direct_bytes);
+        p->ms = now_ms() - t0;
+        return NULL;
     }
-    j->ms = now_ms() - t0;
+    for (uint64_t k = 0; k < p->total; k++) {
+        pthread_mutex_lock(&p->mu);
+        while (p->produced <= k) pthread_cond_wait(&p->cv, &p->mu);
+        const void *ptr = p->ptr[k & 1]; const size_t len = p->len[k & 1];
+        pthread_mutex_unlock(&p->mu);
+        const double t0 = now_ms();
+        fb_md5_update(p->md5, ptr, len);
+        p->ms += now_ms() - t0;
+        pthread_mutex_lock(&p->mu);
+        p->consumed = k + 1;
+        pthread_cond_broadcast(&p->cv);
+        pthread_mutex_unlock(&p->mu);
+    }
     return NULL;
 }
 
@@ -641,10 +710,20 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
     const uint64_t nchunks = (nsamples + chunk - 1) / chunk;
 
     /* MD5 runs beside the GPU for the whole call */
-    Md5Job job = { &c->md5, pcm, fmt, c->bps, (size_t)nsamples * (size_t)c->channels, 0.0 };
+    const int digest_bytes = (c->bps + 7) >> 3;
+    Md5Pipe pipe;
+    memset(&pipe, 0, sizeof pipe);
+    pipe.md5 = &c->md5;
+    pipe.total = nchunks;
+    pthread_mutex_init(&pipe.mu, NULL);
+    pthread_cond_init(&pipe.cv, NULL);
+    if (fmt != FLAKE_B200_PCM_S32 && pcm_bytes_per_sample(fmt) == (size_t)digest_bytes) {
+        pipe.direct = pcm;
+        pipe.direct_bytes = (size_t)nsamples * bps_in;
+    }
     FbMd5 md5_backup = c->md5;
     pthread_t th;
-    const int have_thread = pthread_create(&th, NULL, md5_worker, &job) == 0;
+    const int have_thread = pthread_create(&th, NULL, md5_worker, &pipe) == 0;
 
     fb_cuda_event_record(c->ev_a, c->st);
     uint64_t out_pos = 0;
@@ -654,12 +733,48 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
     const int max0 = c->max_frame_size;
     const FlakeB200Stats stats0 = c->stats;
     int err = 0;
+    int32_t *widen = NULL;          /* only for packed input in a container != ceil(bps/8) */
 
     for (uint64_t k = 0; k <= nchunks && !err; k++) {
         if (k < nchunks) {
             const uint64_t off = k * chunk;
             const uint64_t ns = nsamples - off < chunk ? nsamples - off : chunk;
-            err = lane_submit(c, c->engN, &c->lane[k & 1], (const uint8_t *)pcm + off * bps_in, fmt, ns, counter);
+            FbLane *l = &c->lane[k & 1];
+            const uint8_t *src = (const uint8_t *)pcm + off * bps_in;
+            if (!pipe.direct && have_thread) {
+                /* this lane's previous packed chunk (k-2) must have been hashed */
+                pthread_mutex_lock(&pipe.mu);
+                while (k >= 2 && pipe.consumed < k - 1) pthread_cond_wait(&pipe.cv, &pipe.mu);
+                pthread_mutex_unlock(&pipe.mu);
+            }
+            const void *up; size_t nb; int ufmt;
+            lane_stage(c, l, src, fmt, ns, &up, &nb, &ufmt);
+            if (!pipe.direct) {
+                if (fmt != FLAKE_B200_PCM_S32) {
+                    /* container wider/narrower than the digest layout: widen, then pack */
+                    const size_t cnt = (size_t)ns * (size_t)c->channels, have = pcm_bytes_per_sample(fmt);
+                    if (!widen) widen = (int32_t *)malloc(sizeof(int32_t) * (size_t)chunk * (size_t)c->channels);
+                    if (widen) {
+                        const uint8_t *q = src;
+                        for (size_t i = 0; i < cnt; i++, q += have)
+                            widen[i] = have == 2 ? (int16_t)(q[0] | (q[1] << 8))
+                                     : have == 3 ? (int32_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)(int8_t)q[2] << 16))
+                                     : (int8_t)q[0];
+                        pack_s32(widen, cnt, digest_bytes, (uint8_t *)l->h_pack);
+                        l->pack_bytes = cnt * (size_t)digest_bytes;
+                    } else err = -3;
+                }
+                if (have_thread) {
+                    pthread_mutex_lock(&pipe.mu);
+                    pipe.ptr[k & 1] = l->h_pack; pipe.len[k & 1] = l->pack_bytes;
+                    pipe.produced = k + 1;
+                    pthread_cond_broadcast(&pipe.cv);
+                    pthread_mutex_unlock(&pipe.mu);
+                } else {
+                    fb_md5_update(&c->md5, l->h_pack, l->pack_bytes);
+                }
+            }
+            if (!err) err = lane_launch(c, c->engN, l, up, nb, ufmt, counter);
             /* header number of the next chunk: blocks, or samples when allow_vbs.
              * Under VBS the frame count of a chunk is data dependent, but then
              * allow_vbs is set and the counter advances by samples. */
@@ -684,7 +799,23 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
     }
     fb_cuda_event_record(c->ev_b, c->st);
     fb_cuda_stream_sync(c->st);
-    if (have_thread) pthread_join(th, NULL); else md5_worker(&job);
+    if (have_thread) {
+        if (err && !pipe.direct) {
+            /* let the worker run out: mark every remaining chunk as an empty one */
+            pthread_mutex_lock(&pipe.mu);
+            pipe.len[0] = pipe.len[1] = 0;
+            pipe.produced = pipe.total;
+            pthread_cond_broadcast(&pipe.cv);
+            pthread_mutex_unlock(&pipe.mu);
+        }
+        pthread_join(th, NULL);
+    } else if (pipe.direct) {
+        md5_worker(&pipe);
+    }
+    free(widen);
+    pthread_mutex_destroy(&pipe.mu);
+    pthread_cond_destroy(&pipe.cv);
+    struct { double ms; } job = { pipe.ms };
 
     if (err) {
         /* leave the context as it was before the call */

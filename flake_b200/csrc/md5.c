@@ -5,9 +5,13 @@
 #define ROL(x, s) (((x) << (s)) | ((x) >> (32 - (s))))
 #define F1(b, c, d) ((d) ^ ((b) & ((c) ^ (d))))
 #define F2(b, c, d) ((c) ^ ((d) & ((b) ^ (c))))
-#define F3(b, c, d) ((b) ^ (c) ^ (d))
+#define F3(b, c, d) ((b) ^ ((c) ^ (d)))
 #define F4(b, c, d) ((c) ^ ((b) | ~(d)))
 #define RND(f, a, b, c, d, w, k, s) do { (a) += f((b), (c), (d)) + (w) + (k); (a) = ROL((a), (s)) + (b); } while (0)
+/* round 2: G(b,c,d) = (b & d) | (c & ~d) with disjoint terms, so the part that does not
+ * depend on b (the value produced by the previous step) is added early and only one AND
+ * and one ADD sit between b and the rotate */
+#define RND2(a, b, c, d, w, k, s) do { (a) += ((c) & ~(d)) + (w) + (k); (a) += ((b) & (d)); (a) = ROL((a), (s)) + (b); } while (0)
 
 static void md5_blocks(uint32_t h[4], const uint8_t *p, size_t nblocks)
 {
@@ -25,14 +29,14 @@ static void md5_blocks(uint32_t h[4], const uint8_t *p, size_t nblocks)
         RND(F1, a, b, c, d, w[12], 0x6b901122,  7); RND(F1, d, a, b, c, w[13], 0xfd987193, 12);
         RND(F1, c, d, a, b, w[14], 0xa679438e, 17); RND(F1, b, c, d, a, w[15], 0x49b40821, 22);
 
-        RND(F2, a, b, c, d, w[1],  0xf61e2562,  5); RND(F2, d, a, b, c, w[6],  0xc040b340,  9);
-        RND(F2, c, d, a, b, w[11], 0x265e5a51, 14); RND(F2, b, c, d, a, w[0],  0xe9b6c7aa, 20);
-        RND(F2, a, b, c, d, w[5],  0xd62f105d,  5); RND(F2, d, a, b, c, w[10], 0x02441453,  9);
-        RND(F2, c, d, a, b, w[15], 0xd8a1e681, 14); RND(F2, b, c, d, a, w[4],  0xe7d3fbc8, 20);
-        RND(F2, a, b, c, d, w[9],  0x21e1cde6,  5); RND(F2, d, a, b, c, w[14], 0xc33707d6,  9);
-        RND(F2, c, d, a, b, w[3],  0xf4d50d87, 14); RND(F2, b, c, d, a, w[8],  0x455a14ed, 20);
-        RND(F2, a, b, c, d, w[13], 0xa9e3e905,  5); RND(F2, d, a, b, c, w[2],  0xfcefa3f8,  9);
-        RND(F2, c, d, a, b, w[7],  0x676f02d9, 14); RND(F2, b, c, d, a, w[12], 0x8d2a4c8a, 20);
+        RND2(a, b, c, d, w[1],  0xf61e2562,  5); RND2(d, a, b, c, w[6],  0xc040b340,  9);
+        RND2(c, d, a, b, w[11], 0x265e5a51, 14); RND2(b, c, d, a, w[0],  0xe9b6c7aa, 20);
+        RND2(a, b, c, d, w[5],  0xd62f105d,  5); RND2(d, a, b, c, w[10], 0x02441453,  9);
+        RND2(c, d, a, b, w[15], 0xd8a1e681, 14); RND2(b, c, d, a, w[4],  0xe7d3fbc8, 20);
+        RND2(a, b, c, d, w[9],  0x21e1cde6,  5); RND2(d, a, b, c, w[14], 0xc33707d6,  9);
+        RND2(c, d, a, b, w[3],  0xf4d50d87, 14); RND2(b, c, d, a, w[8],  0x455a14ed, 20);
+        RND2(a, b, c, d, w[13], 0xa9e3e905,  5); RND2(d, a, b, c, w[2],  0xfcefa3f8,  9);
+        RND2(c, d, a, b, w[7],  0x676f02d9, 14); RND2(b, c, d, a, w[12], 0x8d2a4c8a, 20);
 
         RND(F3, a, b, c, d, w[5],  0xfffa3942,  4); RND(F3, d, a, b, c, w[8],  0x8771f681, 11);
         RND(F3, c, d, a, b, w[11], 0x6d9d6122, 16); RND(F3, b, c, d, a, w[14], 0xfde5380c, 23);

@@ -92,6 +92,24 @@ def test_packed_pcm_ingest(fmt, bps, gpu_lib):
     assert a.payload == b.payload and a.streaminfo == b.streaminfo
 
 
+def test_out_of_range_int32_input_is_passed_through(gpu_lib, oracle):
+    """flake_encode_frame takes int32: samples wider than bits_per_sample are the caller's bug,
+    but the encoder must still see exactly those values (the host layer packs to
+    ceil(bps/8) bytes for the upload only when that is lossless) and the MD5 must hash the
+    low bytes like md5.c:296-309."""
+    pcm = synth.synth_pcm(4096 * 3, 2, 16, 44100, seed=5)
+    pcm[1000:1100] *= 5          # beyond 16 bits
+    pcm[5000, 1] = 1 << 20
+    for level in (2, 8):
+        got = api.encode_batch(gpu_lib, pcm, 44100, 16, level, chunk_blocks=2)
+        want, flen, fbs, mx = oracle.encode_stream(pcm, 44100, 16, level)
+        assert got.payload == want
+        p = oracle.make_params(2, 44100, 16, level, pcm.shape[0])
+        assert got.streaminfo == oracle.streaminfo(p, mx, oracle.md5_pcm(pcm, 16))
+        blk = api.encode_per_block(gpu_lib, pcm, 44100, 16, level)
+        assert blk.payload == want and blk.streaminfo == got.streaminfo
+
+
 def test_matches_compiled_reference(gpu_lib, oracle):
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not built (needs /root/reference at build time)")

@@ -42,6 +42,7 @@ struct FbEngine {
     uint32_t *d_frame_len;
     uint64_t *d_frame_off;
     uint32_t *d_vbs_sizes, *d_vbs_counts;
+    uint16_t *d_xpow32;             /* x^(32 j) mod P, CRC-16 chunk merge (k_pack) */
     int lpc_smem_doubles, search_smem_ints, pack_smem_words;
     uint64_t launches;
     /* optional per-kernel CUDA-event timing (bench.py roofline) */
@@ -130,6 +131,22 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
         const uint64_t capw = (capb + 3u) >> 2;
         e->pack_smem_words = (capw * 4u <= FB_SMEM_BUDGET) ? (int)capw : 0;
     }
+    {
+        /* x^(32 j) mod (x^16 + x^15 + x^2 + 1): j zero words appended to a CRC (crc.c:24-46) */
+        const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
+        const size_t nent = (size_t)((capb + 3u) >> 2) + 64;
+        uint16_t *tab = (uint16_t *)malloc(nent * sizeof(uint16_t));
+        if (!tab) { set_err(err, errlen, "out of host memory", cudaSuccess); fb_engine_destroy(e); return nullptr; }
+        uint32_t r = 1;
+        for (size_t j = 0; j < nent; j++) {
+            tab[j] = (uint16_t)r;
+            for (int b = 0; b < 32; b++) r = (r & 0x8000u) ? ((r << 1) ^ 0x8005u) & 0xffffu : (r << 1) & 0xffffu;
+        }
+        cudaError_t ce_ = cudaMalloc((void **)&e->d_xpow32, nent * sizeof(uint16_t));
+        if (ce_ == cudaSuccess) ce_ = cudaMemcpy(e->d_xpow32, tab, nent * sizeof(uint16_t), cudaMemcpyHostToDevice);
+        free(tab);
+        if (ce_ != cudaSuccess) { set_err(err, errlen, "CRC table upload failed", ce_); fb_engine_destroy(e); return nullptr; }
+    }
     cudaFuncSetAttribute(k_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, e->lpc_smem_doubles * 8);
     cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
     cudaFuncSetAttribute(k_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
@@ -146,7 +163,7 @@ extern "C" void fb_engine_destroy(FbEngine *e)
     cudaFree(e->d_frames); cudaFree(e->d_nframes); cudaFree(e->d_subs); cudaFree(e->d_modes);
     cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
     cudaFree(e->d_win); cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
-    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts);
+    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32);
     if (e->tev[0][0])
         for (int p = 0; p < FB_TIMING_RING; p++)
             for (int i = 0; i <= FB_NUM_STAGES; i++) cudaEventDestroy(e->tev[p][i]);
@@ -223,7 +240,7 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     FB_MARK(4);
     FB_LAUNCH(k_pack, dim3(grid_frames), dim3(FB_PACK_THREADS), (size_t)e->pack_smem_words * 4, st,
               cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
-              flen, d_frame_bs, e->d_verbatim, e->pack_smem_words);
+              flen, d_frame_bs, e->d_verbatim, e->pack_smem_words, e->d_xpow32);
     FB_MARK(5);
     FB_LAUNCH(k_offsets, dim3(1), dim3(1024), 0, st,
               e->d_nframes, flen, e->d_frame_off, d_summary, e->d_verbatim);

@@ -58,64 +58,78 @@ __device__ __forceinline__ uint32_t fb_gf16_xpow8(uint32_t nbytes)
 }
 
 /* ---------------- MSB-first bit emitter -------------------------------- */
+/* 64-bit left-aligned accumulator: `fill` (< 32 between calls) bits are pending in the top
+ * of `acc`; whole 32-bit words are emitted as soon as they are complete.  The staging buffer
+ * holds big-endian bytes and starts zeroed, so all-zero words are skipped.  The first word a
+ * writer touches and its last partial word may be shared with the neighbouring writers and
+ * are merged with atomicOr; every word in between is covered by this writer alone. */
 struct FbBitPut {
-    uint32_t *buf;      /* staging buffer as 32-bit words holding big-endian bytes */
+    uint32_t *buf;
     uint32_t capw;      /* capacity in words */
     uint32_t widx;      /* current word */
-    uint32_t cur;       /* bits gathered for the current word (MSB first) */
-    int fill;           /* bits of `cur` in use, 0..31 */
-    bool boundary;      /* current word may be shared with another thread */
+    unsigned long long acc;
+    uint32_t fill;
+    bool boundary;
 };
 
 __device__ __forceinline__ void fb_bp_init(FbBitPut &b, uint32_t *buf, uint32_t capw, uint64_t bitpos)
 {
     b.buf = buf; b.capw = capw;
     b.widx = (uint32_t)(bitpos >> 5);
-    b.fill = (int)(bitpos & 31u);
-    b.cur = 0;
+    b.fill = (uint32_t)(bitpos & 31u);
+    b.acc = 0;
     b.boundary = true;
 }
-__device__ __forceinline__ void fb_bp_flush_word(FbBitPut &b, bool last)
+__device__ __forceinline__ void fb_bp_emit(FbBitPut &b)
 {
-    if (b.cur && b.widx < b.capw) {
-        const uint32_t be = __byte_perm(b.cur, 0, 0x0123);
-        if (b.boundary || last) atomicOr(&b.buf[b.widx], be);
+    const uint32_t w = (uint32_t)(b.acc >> 32);
+    if (w && b.widx < b.capw) {
+        const uint32_t be = __byte_perm(w, 0, 0x0123);
+        if (b.boundary) atomicOr(&b.buf[b.widx], be);
         else b.buf[b.widx] = be;
     }
-    b.widx++; b.cur = 0; b.fill = 0; b.boundary = false;
+    b.acc <<= 32; b.widx++; b.fill -= 32; b.boundary = false;
 }
 /* nbits in 1..32, val < 2^nbits */
-__device__ __forceinline__ void fb_bp_put(FbBitPut &b, int nbits, uint32_t val)
+__device__ __forceinline__ void fb_bp_put(FbBitPut &b, uint32_t nbits, uint32_t val)
 {
-    const int space = 32 - b.fill;
-    if (nbits < space) {
-        b.cur |= val << (space - nbits);
-        b.fill += nbits;
-    } else {
-        const int rem = nbits - space;
-        b.cur |= rem < 32 ? (val >> rem) : 0u;
-        fb_bp_flush_word(b, false);
-        if (rem) { b.cur = val << (32 - rem); b.fill = rem; }
-    }
+    b.acc |= (unsigned long long)val << (64u - b.fill - nbits);
+    b.fill += nbits;
+    if (b.fill >= 32u) fb_bp_emit(b);
 }
 __device__ __forceinline__ void fb_bp_skip(FbBitPut &b, uint32_t nzeros)
 {
-    uint64_t f = (uint64_t)b.fill + nzeros;
-    if (f >= 32) {
-        fb_bp_flush_word(b, false);
-        b.widx += (uint32_t)(f >> 5) - 1u;
-        f &= 31u;
+    const unsigned long long f = (unsigned long long)b.fill + nzeros;
+    if (f >= 32u) {
+        b.fill = 32u;                       /* close the current word ... */
+        fb_bp_emit(b);                      /* (acc has no bits beyond it: fill was < 32) */
+        b.widx += (uint32_t)(f >> 5) - 1u;  /* ... and jump over the all-zero ones */
+        b.fill = (uint32_t)(f & 31u);
+    } else {
+        b.fill = (uint32_t)f;
     }
-    b.fill = (int)f;
 }
 __device__ __forceinline__ void fb_bp_finish(FbBitPut &b)
 {
-    if (b.fill) fb_bp_flush_word(b, true);
+    const uint32_t w = (uint32_t)(b.acc >> 32);
+    if (b.fill && w && b.widx < b.capw) atomicOr(&b.buf[b.widx], __byte_perm(w, 0, 0x0123));
 }
 __device__ __forceinline__ void fb_bp_put_signed(FbBitPut &b, int nbits, int32_t v)
 {
-    if (nbits >= 32) { fb_bp_put(b, 32, (uint32_t)v); return; }
-    fb_bp_put(b, nbits, (uint32_t)v & ((1u << nbits) - 1u));
+    if (nbits >= 32) { fb_bp_put(b, 32u, (uint32_t)v); return; }
+    fb_bp_put(b, (uint32_t)nbits, (uint32_t)v & ((1u << nbits) - 1u));
+}
+/* Rice code of zig-zag value u with parameter k (bitio.h:120-141): u>>k zeros, a one, k low bits */
+__device__ __forceinline__ void fb_bp_put_rice(FbBitPut &b, uint32_t u, uint32_t k)
+{
+    const uint32_t q = u >> k;
+    const uint32_t low = (1u << k) | (u & ((1u << k) - 1u));
+    if (q + k + 1u <= 32u) {
+        fb_bp_put(b, q + k + 1u, low);      /* leading zeros ride along */
+    } else {
+        fb_bp_skip(b, q);
+        fb_bp_put(b, k + 1u, low);
+    }
 }
 
 /* ---------------- per-subframe geometry -------------------------------- */
@@ -140,36 +154,23 @@ __device__ __forceinline__ FbSubLayout fb_sub_layout(const FbSub *sb, int n, boo
     return L;
 }
 
-/* bits of sample i's token (Rice code [+ partition parameter]) */
-__device__ __forceinline__ uint32_t fb_token_bits(const FbSubLayout &L, const FbSub *sb,
-                                                  const int32_t *data, int i)
-{
-    if (L.type == 1) return (uint32_t)L.obits;
-    if (L.type == 0 || i < L.order) return 0;
-    const int p = i / L.psize;
-    const int k = sb->params[p];
-    const uint32_t u = fb_zigzag(data[i]);
-    uint32_t bits = (u >> k) + 1u + (uint32_t)k;
-    if (p > 0 && i == p * L.psize) bits += (uint32_t)L.pbits;
-    return bits;
-}
-
 /*
  * frames[f] -> staged bytes at slots + frames[f].slot, frame_len[f].
  * smem_words: capacity of the dynamic shared staging buffer (0: write the
- * global slot directly).
+ * global slot directly).  xpow32[j] = x^(32 j) mod P for the CRC-16 merge.
  */
 __global__ void __launch_bounds__(FB_PACK_THREADS)
 k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
        const int32_t *res, FbSub *subs, const uint8_t *ch_modes, uint8_t *slots,
-       uint32_t *frame_len, uint32_t *frame_bs, uint32_t *verbatim_count, int smem_words)
+       uint32_t *frame_len, uint32_t *frame_bs, uint32_t *verbatim_count, int smem_words,
+       const uint16_t *xpow32)
 {
     FB_DYN_SMEM(dyn);
     __shared__ uint32_t scan_scratch[33];
     __shared__ uint16_t crc_tab[4][256];
-    __shared__ uint32_t crc_part[32];
     __shared__ uint32_t s_hdr_len;
     __shared__ uint8_t s_hdr[24];
+    __shared__ uint8_t s_params[256];
 
     const uint32_t f = blockIdx.x;
     if (f >= *nframes) return;
@@ -251,38 +252,70 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
             const FbSubLayout L = fb_sub_layout(sb, n, verbatim);
             const size_t off = (size_t)fr.start * C + (size_t)c * n;
             const int32_t *data = (L.type == 1 || L.type == 0) ? smp + off : res + off;
+            const bool rice = (L.type == 8 || L.type == 32);
 
-            /* size my run, scan */
+            /* Rice parameters of this subframe into shared memory */
+            if (rice) for (int j = tid; j < (1 << L.porder); j += T) s_params[j] = sb->params[j];
+            __syncthreads();
+
+            /* size my run (partition index tracked incrementally), then scan */
+            const int jbeg = rice ? max(i0, L.order) : i0;
             uint32_t mybits = 0;
-            if (L.type == 1) mybits = (uint32_t)(i1 - i0) * (uint32_t)L.obits;
-            else if (L.type != 0)
-                for (int i = i0; i < i1; i++) mybits += fb_token_bits(L, sb, data, i);
+            if (L.type == 1) {
+                mybits = (uint32_t)(i1 - i0) * (uint32_t)L.obits;
+            } else if (rice && jbeg < i1) {
+                int p = jbeg / L.psize;
+                int nb = (p + 1) * L.psize;
+                uint32_t k = s_params[p];
+                if (p > 0 && jbeg == p * L.psize) mybits += (uint32_t)L.pbits;
+                for (int i = jbeg; i < i1; i++) {
+                    if (i == nb) { p++; nb += L.psize; k = s_params[p]; mybits += (uint32_t)L.pbits; }
+                    mybits += (fb_zigzag(data[i]) >> k) + 1u + k;
+                }
+            }
             uint32_t sub_tokens;
             const uint32_t myoff = fb_block_exscan_u32(mybits, scan_scratch, &sub_tokens);
 
-            /* preamble (thread 0) */
-            if (tid == 0) {
-                FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos);
-                int code = L.type;
-                if (L.type == 8) code = 8 | L.order;
-                if (L.type == 32) code = 32 | (L.order - 1);
-                fb_bp_put(b, 7, (uint32_t)code);             /* leading 0 + 6-bit type */
-                if (L.wasted) { fb_bp_put(b, 1, 1); fb_bp_skip(b, (uint32_t)(L.wasted - 1)); fb_bp_put(b, 1, 1); }
-                else fb_bp_put(b, 1, 0);
-                if (L.type == 0) {
-                    fb_bp_put_signed(b, L.obits, sb->first);
-                } else if (L.type == 8 || L.type == 32) {
-                    for (int i = 0; i < L.order; i++) fb_bp_put_signed(b, L.obits, data[i]);
-                    if (L.type == 32) {
-                        fb_bp_put(b, 4, 14);
-                        fb_bp_put_signed(b, 5, L.shift);
-                        for (int i = 0; i < L.order; i++) fb_bp_put_signed(b, 15, sb->coefs[i]);
+            /* preamble: fixed-width fields at known offsets, one writer per field
+             * (every field is <= 32 bits, so both words it can touch are merged atomically) */
+            {
+                const uint64_t pre0 = bitpos + 8u + (uint32_t)L.wasted;          /* after the subframe header */
+                if (tid == 0) {
+                    FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos);
+                    int code = L.type;
+                    if (L.type == 8) code = 8 | L.order;
+                    if (L.type == 32) code = 32 | (L.order - 1);
+                    fb_bp_put(b, 7, (uint32_t)code);         /* leading 0 + 6-bit type */
+                    if (L.wasted) { fb_bp_put(b, 1, 1); fb_bp_skip(b, (uint32_t)(L.wasted - 1)); fb_bp_put(b, 1, 1); }
+                    else fb_bp_put(b, 1, 0);
+                    if (L.type == 0) fb_bp_put_signed(b, L.obits, sb->first);
+                    fb_bp_finish(b);
+                    if (rice) {
+                        uint64_t at = pre0 + (uint64_t)(L.order * L.obits);
+                        if (L.type == 32) {
+                            fb_bp_init(b, wbuf, capw, at);
+                            fb_bp_put(b, 4, 14);
+                            fb_bp_put_signed(b, 5, L.shift);
+                            fb_bp_finish(b);
+                            at += 9u + (uint64_t)L.order * 15u;
+                        }
+                        fb_bp_init(b, wbuf, capw, at);
+                        fb_bp_put(b, 2, (uint32_t)L.method);
+                        fb_bp_put(b, 4, (uint32_t)L.porder);
+                        fb_bp_put(b, (uint32_t)L.pbits, s_params[0]);
+                        fb_bp_finish(b);
                     }
-                    fb_bp_put(b, 2, (uint32_t)L.method);
-                    fb_bp_put(b, 4, (uint32_t)L.porder);
-                    fb_bp_put(b, L.pbits, sb->params[0]);
+                } else if (rice && tid >= 32 && tid < 32 + L.order) {              /* warm-up samples */
+                    const int i = tid - 32;
+                    FbBitPut b; fb_bp_init(b, wbuf, capw, pre0 + (uint64_t)(i * L.obits));
+                    fb_bp_put_signed(b, L.obits, data[i]);
+                    fb_bp_finish(b);
+                } else if (L.type == 32 && tid >= 64 && tid < 64 + L.order) {      /* LPC coefficients */
+                    const int i = tid - 64;
+                    FbBitPut b; fb_bp_init(b, wbuf, capw, pre0 + (uint64_t)(L.order * L.obits) + 9u + (uint64_t)i * 15u);
+                    fb_bp_put_signed(b, 15, sb->coefs[i]);
+                    fb_bp_finish(b);
                 }
-                fb_bp_finish(b);
             }
             /* my tokens */
             if (mybits) {
@@ -290,18 +323,19 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
                 if (L.type == 1) {
                     for (int i = i0; i < i1; i++) fb_bp_put_signed(b, L.obits, data[i]);
                 } else {
-                    for (int i = max(i0, L.order); i < i1; i++) {
-                        const int p = i / L.psize;
-                        const int k = sb->params[p];
-                        if (p > 0 && i == p * L.psize) fb_bp_put(b, L.pbits, (uint32_t)k);
-                        const uint32_t u = fb_zigzag(data[i]);
-                        fb_bp_skip(b, u >> k);
-                        fb_bp_put(b, k + 1, (1u << k) | (u & ((1u << k) - 1u)));
+                    int p = jbeg / L.psize;
+                    int nb = (p + 1) * L.psize;
+                    uint32_t k = s_params[p];
+                    if (p > 0 && jbeg == p * L.psize) fb_bp_put(b, (uint32_t)L.pbits, k);
+                    for (int i = jbeg; i < i1; i++) {
+                        if (i == nb) { p++; nb += L.psize; k = s_params[p]; fb_bp_put(b, (uint32_t)L.pbits, k); }
+                        fb_bp_put_rice(b, fb_zigzag(data[i]), k);
                     }
                 }
                 fb_bp_finish(b);
             }
             bitpos += (uint64_t)L.preamble_bits + sub_tokens;
+            __syncthreads();                         /* s_params is re-used by the next channel */
         }
         total_bits = bitpos;
         const uint64_t nbytes = ((total_bits + 7u) >> 3) + 2u;
@@ -318,20 +352,22 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     uint32_t body = (uint32_t)((total_bits + 7u) >> 3);      /* bytes before the CRC-16 */
     if (body + 2u > cap_bytes) body = cap_bytes - 2u;         /* cannot happen for <= 24-bit input */
 
-    /* ---- CRC-16 over the body: right-aligned word chunks ------------------- */
+    /* ---- CRC-16 over the body (crc.c:59-92) ---------------------------------------------
+     * The body is cut into T right-aligned chunks of `per` words (virtual zero words in
+     * front leave a zero-initialised CRC unchanged, and so do the zero bytes that pad the
+     * first real word); each thread runs slicing-by-4 over its chunk and the chunk CRCs are
+     * merged pairwise: crc(A || B) = crc(A) * x^(8 |B|) + crc(B) over GF(2)[x]/P, with the
+     * multipliers x^(32 * per * 2^level) read from the engine's table. */
     {
-        const uint32_t nwords = (body + 3u) >> 2;            /* trailing pad bytes are zero... */
-        const uint32_t padbytes = nwords * 4u - body;        /* ...so treat them as leading zeros */
-        /* chunking is done on a byte stream shifted right by padbytes: equivalent to
-         * prepending zero bytes, which leave a zero-initialised CRC unchanged. */
-        const uint32_t per = (nwords + (uint32_t)T - 1u) / (uint32_t)T;   /* words per thread */
-        const uint32_t lead = per * (uint32_t)T - nwords;                 /* virtual zero words in front */
+        const uint32_t nwords = (body + 3u) >> 2;
+        const uint32_t padbytes = nwords * 4u - body;
+        const uint32_t per = (nwords + (uint32_t)T - 1u) / (uint32_t)T;
+        const uint32_t lead = per * (uint32_t)T - nwords;
         uint32_t crc = 0;
         for (uint32_t j = 0; j < per; j++) {
-            const uint32_t vw = (uint32_t)tid * per + j;                  /* virtual word index */
+            const uint32_t vw = (uint32_t)tid * per + j;
             if (vw < lead) continue;
-            const uint32_t wi = vw - lead;                                /* index in shifted stream */
-            /* shifted stream word wi = bytes [4*wi - padbytes, 4*wi - padbytes + 4) of the body */
+            const uint32_t wi = vw - lead;
             uint32_t word;
             if (padbytes == 0) {
                 word = __byte_perm(wbuf[wi], 0, 0x0123);
@@ -344,27 +380,25 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
             crc = (uint32_t)crc_tab[3][x >> 24] ^ (uint32_t)crc_tab[2][(x >> 16) & 255u] ^
                   (uint32_t)crc_tab[1][(x >> 8) & 255u] ^ (uint32_t)crc_tab[0][x & 255u];
         }
-        /* combine: thread t is followed by (T-1-t) chunks of `per` words */
-        uint32_t m = fb_gf16_xpow8(per * 4u);
         const int lane = tid & 31, warp = tid >> 5;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t right = __shfl_down_sync(FB_FULL_MASK, crc, o);
-            if ((lane & (2 * o - 1)) == 0) crc = fb_gf16_mul(crc, m) ^ right;
-            m = fb_gf16_mul(m, m);
+        for (int l = 0; l < 5; l++) {
+            const uint32_t m = xpow32[per << l];
+            const uint32_t right = __shfl_down_sync(FB_FULL_MASK, crc, 1u << l);
+            if ((lane & ((2 << l) - 1)) == 0) crc = fb_gf16_mul(crc, m) ^ right;
         }
-        if (lane == 0) crc_part[warp] = crc;
+        if (lane == 0) scan_scratch[warp] = crc;
         __syncthreads();
         if (tid == 0) {
-            const int nw = T >> 5;
+            /* warps in order: acc = acc * x^(8 * bytes per warp) + next */
+            const uint32_t m = xpow32[per << 5];
             uint32_t acc = 0;
-            for (int w = 0; w < nw; w++) acc = fb_gf16_mul(acc, m) ^ crc_part[w];
-            /* append big-endian */
+            for (int w = 0; w < (T >> 5); w++) acc = fb_gf16_mul(acc, m) ^ scan_scratch[w];
             FbBitPut b; fb_bp_init(b, wbuf, capw, (uint64_t)body * 8u);
             fb_bp_put(b, 16, acc);
             fb_bp_finish(b);
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     const uint32_t nbytes = body + 2u;
     if (in_smem) {

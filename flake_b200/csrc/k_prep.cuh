@@ -148,6 +148,46 @@ k_frames_vbs(FbConfig cfg, uint32_t nsamples, uint32_t first_number,
 /* ------------------------------------------------------------------ */
 /* prepare: one CTA per frame                                           */
 /* ------------------------------------------------------------------ */
+#define FB_PREP_RUN 8
+
+/* Samples i-2 .. i+7 of a stereo frame into lw[0..9] / rw[0..9] (index 2 = sample i);
+ * positions outside [0, n) read as 0.  `ibase` = interleaved element index of the frame's
+ * sample 0.  Whole in-range runs of packed s16 (two 16-byte loads) and int32 (four) are
+ * loaded vectorised when the address allows. */
+__device__ __forceinline__ void fb_load_stereo_run(const void *pcm, int fmt, size_t ibase, int i, int n,
+                                                   int32_t *lw, int32_t *rw)
+{
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int idx = i - 2 + k;
+        const bool ok = idx >= 0 && idx < n;
+        lw[k] = ok ? fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)idx) : 0;
+        rw[k] = ok ? fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)idx + 1) : 0;
+    }
+    const size_t e0 = ibase + 2 * (size_t)i;
+    if (i + FB_PREP_RUN <= n && fmt == FB_PCM_S16LE && ((((size_t)pcm) + e0 * 2) & 15u) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>((const uint8_t *)pcm + e0 * 2);
+        const uint4 a = src[0], b = src[1];
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) { lw[2 + k] = (int32_t)(w[k] << 16) >> 16; rw[2 + k] = (int32_t)w[k] >> 16; }
+    } else if (i + FB_PREP_RUN <= n && fmt == FB_PCM_S32 && ((((size_t)pcm) + e0 * 4) & 15u) == 0) {
+        const int4 *src = reinterpret_cast<const int4 *>((const uint8_t *)pcm + e0 * 4);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int4 v = src[g];
+            lw[2 + 2 * g] = v.x; rw[2 + 2 * g] = v.y; lw[3 + 2 * g] = v.z; rw[3 + 2 * g] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < FB_PREP_RUN; k++) {
+            const bool ok = i + k < n;
+            lw[2 + k] = ok ? fb_load_pcm(pcm, fmt, e0 + 2 * (size_t)k) : 0;
+            rw[2 + k] = ok ? fb_load_pcm(pcm, fmt, e0 + 2 * (size_t)k + 1) : 0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FB_PREP_THREADS)
 k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint32_t *nframes,
        int32_t *smp, FbSub *subs, uint8_t *ch_modes)
@@ -168,19 +208,21 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
         mode = 1;                                            /* LEFT_RIGHT */
         if (n > 32 && cfg.stereo_method == 1) {
             uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int i = 2 + tid; i < n; i += T) {
-                const size_t p = ibase + 2 * (size_t)i;
-                int32_t l0 = fb_load_pcm(pcm, fmt, p),     r0 = fb_load_pcm(pcm, fmt, p + 1);
-                int32_t l1 = fb_load_pcm(pcm, fmt, p - 2), r1 = fb_load_pcm(pcm, fmt, p - 1);
-                int32_t l2 = fb_load_pcm(pcm, fmt, p - 4), r2 = fb_load_pcm(pcm, fmt, p - 3);
-                int32_t lt = (int32_t)((uint32_t)l0 - 2u * (uint32_t)l1 + (uint32_t)l2);
-                int32_t rt = (int32_t)((uint32_t)r0 - 2u * (uint32_t)r1 + (uint32_t)r2);
-                int32_t m = (int32_t)((uint32_t)lt + (uint32_t)rt) >> 1;
-                int32_t d = (int32_t)((uint32_t)lt - (uint32_t)rt);
-                s0 += (uint64_t)(int64_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
-                s1 += (uint64_t)(int64_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
-                s2 += (uint64_t)(int64_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);
-                s3 += (uint64_t)(int64_t)(d < 0 ? (int32_t)(0u - (uint32_t)d) : d);
+            for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
+                int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2];
+                fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
+#pragma unroll
+                for (int k = 0; k < FB_PREP_RUN; k++) {
+                    if (i + k < 2 || i + k >= n) continue;
+                    const int32_t lt = (int32_t)((uint32_t)lw[k + 2] - 2u * (uint32_t)lw[k + 1] + (uint32_t)lw[k]);
+                    const int32_t rt = (int32_t)((uint32_t)rw[k + 2] - 2u * (uint32_t)rw[k + 1] + (uint32_t)rw[k]);
+                    const int32_t m = (int32_t)((uint32_t)lt + (uint32_t)rt) >> 1;
+                    const int32_t d = (int32_t)((uint32_t)lt - (uint32_t)rt);
+                    s0 += (uint64_t)(int64_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
+                    s1 += (uint64_t)(int64_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
+                    s2 += (uint64_t)(int64_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);
+                    s3 += (uint64_t)(int64_t)(d < 0 ? (int32_t)(0u - (uint32_t)d) : d);
+                }
             }
             s0 = fb_block_sum_u64(s0, red);
             s1 = fb_block_sum_u64(s1, red);
@@ -221,18 +263,34 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
         else if (mode == 8) { first[0] = l; first[1] = (int32_t)((uint32_t)l - (uint32_t)r); }
         else if (mode == 9) { first[0] = (int32_t)((uint32_t)l - (uint32_t)r); first[1] = r; }
         else                { first[0] = l; first[1] = r; }
-        for (int i = tid; i < n; i += T) {
-            l = fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)i);
-            r = fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)i + 1);
-            int32_t a, b;
-            if (mode == 10)     { a = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; b = (int32_t)((uint32_t)l - (uint32_t)r); }
-            else if (mode == 8) { a = l; b = (int32_t)((uint32_t)l - (uint32_t)r); }
-            else if (mode == 9) { a = (int32_t)((uint32_t)l - (uint32_t)r); b = r; }
-            else                { a = l; b = r; }
-            plane[i] = a; plane[n + i] = b;
-            orv[0] |= (uint32_t)a; orv[1] |= (uint32_t)b;
-            ne[0] |= (uint32_t)(a != first[0]); ne[1] |= (uint32_t)(b != first[1]);
-            mx[0] = max(mx[0], (uint32_t)(a < 0 ? ~a : a)); mx[1] = max(mx[1], (uint32_t)(b < 0 ? ~b : b));
+        const bool planes_aligned = ((((size_t)plane) | ((size_t)n * 4u)) & 15u) == 0;
+        for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
+            int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2], av[FB_PREP_RUN], bv[FB_PREP_RUN];
+            fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
+#pragma unroll
+            for (int k = 0; k < FB_PREP_RUN; k++) {
+                l = lw[k + 2]; r = rw[k + 2];
+                int32_t a, b;
+                if (mode == 10)     { a = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; b = (int32_t)((uint32_t)l - (uint32_t)r); }
+                else if (mode == 8) { a = l; b = (int32_t)((uint32_t)l - (uint32_t)r); }
+                else if (mode == 9) { a = (int32_t)((uint32_t)l - (uint32_t)r); b = r; }
+                else                { a = l; b = r; }
+                av[k] = a; bv[k] = b;
+                if (i + k < n) {
+                    orv[0] |= (uint32_t)a; orv[1] |= (uint32_t)b;
+                    ne[0] |= (uint32_t)(a != first[0]); ne[1] |= (uint32_t)(b != first[1]);
+                    mx[0] = max(mx[0], (uint32_t)(a < 0 ? ~a : a)); mx[1] = max(mx[1], (uint32_t)(b < 0 ? ~b : b));
+                }
+            }
+            if (i + FB_PREP_RUN <= n && planes_aligned) {
+                int4 *pa = reinterpret_cast<int4 *>(plane + i), *pb = reinterpret_cast<int4 *>(plane + n + i);
+                pa[0] = make_int4(av[0], av[1], av[2], av[3]); pa[1] = make_int4(av[4], av[5], av[6], av[7]);
+                pb[0] = make_int4(bv[0], bv[1], bv[2], bv[3]); pb[1] = make_int4(bv[4], bv[5], bv[6], bv[7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < FB_PREP_RUN; k++)
+                    if (i + k < n) { plane[i + k] = av[k]; plane[n + i + k] = bv[k]; }
+            }
         }
     } else {
 #pragma unroll
@@ -266,7 +324,12 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
             }
             if (wasted) {
                 int32_t *pl = plane + (size_t)c * n;
-                for (int i = tid; i < n; i += T) pl[i] >>= wasted;   /* own elements only */
+                if (C == 2) {                                       /* own elements only: same runs as above */
+                    for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN)
+                        for (int k = 0; k < FB_PREP_RUN && i + k < n; k++) pl[i + k] >>= wasted;
+                } else {
+                    for (int i = tid; i < n; i += T) pl[i] >>= wasted;
+                }
             }
             if (tid == 0) {
                 FbSub *sb = &subs[(size_t)f * C + c];

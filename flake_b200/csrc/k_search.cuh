@@ -130,7 +130,7 @@ __device__ __forceinline__ uint32_t fb_eval_finish(FbSearchShared &S, int n, int
  * res_out != NULL: also store the residual (warm-up = samples).
  * store   != NULL: also record method / porder / params for the packer.
  */
-__device__ uint32_t fb_evaluate(FbSearchShared &S, const int32_t *x, int n, int is_lpc, int order,
+__device__ __noinline__ uint32_t fb_evaluate(FbSearchShared &S, const int32_t *x, int n, int is_lpc, int order,
                                 int obits, int pmin_cfg, int pmax_cfg,
                                 int32_t *res_out, FbSub *store)
 {

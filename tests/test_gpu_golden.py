@@ -125,3 +125,21 @@ def test_unmodified_reference_cli_links_and_matches(gpu_lib, oracle, tmp_path):
         subprocess.run([cli, "-q", level, str(wav), "-o", str(a)], check=True)
         subprocess.run([pyoracle.REF_CLI, "-q", level, str(wav), "-o", str(b)], check=True)
         assert a.read_bytes() == b.read_bytes()
+
+
+def test_plain_c_caller(gpu_lib, oracle, tmp_path):
+    """tests/c/batch_example.c: a C program in the shape of util/api_example.c, compiled against
+    include/*.h and linked with libflake.so; per-block and batch outputs must be one valid file."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "batch_example"
+    subprocess.run(["gcc", "-O1", os.path.join(root, "tests", "c", "batch_example.c"),
+                    "-I", os.path.join(root, "include"), "-L", os.path.join(root, "flake_b200", "lib"),
+                    "-lflake", "-Wl,-rpath," + os.path.join(root, "flake_b200", "lib"), "-o", str(exe)],
+                   check=True)
+    a, b = tmp_path / "a.flac", tmp_path / "b.flac"
+    subprocess.run([str(exe), str(a), str(b), "8"], check=True)
+    da, db = a.read_bytes(), b.read_bytes()
+    assert da == db
+    dec, info = oracle.decode(da)
+    assert info.md5_ok == 1 and info.decoded_samples == 4096 * 20 + 1234

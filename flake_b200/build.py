@@ -44,19 +44,23 @@ def _csrc_files():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
 
 
-def build_product(force: bool = False) -> str:
-    os.makedirs(LIBDIR, exist_ok=True)
-    out = os.path.join(LIBDIR, "libflake.so")
+def build_product(force: bool = False, variant: str = "", defines=()) -> str:
+    """The shipped library.  `variant`/`defines` (dev only, tools/variants.py) build
+    flake_b200/lib/var/libflake_<variant>.so with extra -D flags for A/B timing on the GPU."""
+    libdir = os.path.join(LIBDIR, "var", variant) if variant else LIBDIR
+    os.makedirs(libdir, exist_ok=True)
+    out = os.path.join(libdir, "libflake.so")
     inc = os.path.join(ROOT, "include")
     srcs = _csrc_files() + [os.path.join(inc, f) for f in os.listdir(inc)]
     if not force and not _newer(out, srcs):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    obj_cu = os.path.join(LIBDIR, "engine.o")
-    _run([nvcc] + NVCC_FLAGS + ["-I", inc, "-c", os.path.join(CSRC, "engine.cu"), "-o", obj_cu])
+    obj_cu = os.path.join(libdir, "engine.o")
+    _run([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] +
+         ["-I", inc, "-c", os.path.join(CSRC, "engine.cu"), "-o", obj_cu])
     objs = [obj_cu]
     for c in ("flake_host.c", "md5.c"):
-        o = os.path.join(LIBDIR, c.replace(".c", ".o"))
+        o = os.path.join(libdir, c.replace(".c", ".o"))
         _run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-I", inc, "-I", CSRC,
               "-c", os.path.join(CSRC, c), "-o", o])
         objs.append(o)

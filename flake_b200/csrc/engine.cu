@@ -43,7 +43,7 @@ struct FbEngine {
     uint64_t *d_frame_off;
     uint32_t *d_vbs_sizes, *d_vbs_counts;
     uint16_t *d_xpow32;             /* x^(32 j) mod P, CRC-16 chunk merge (k_pack) */
-    int lpc_smem_doubles, search_smem_ints, pack_smem_words;
+    int search_smem_ints, pack_smem_words;
     uint64_t launches;
     /* optional per-kernel CUDA-event timing (bench.py roofline) */
     int timing_on, timing_passes;
@@ -124,7 +124,6 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     }
 
     /* shared-memory staging where a whole block fits */
-    e->lpc_smem_doubles = FB_LPC_RING + cfg->max_order * FB_MAX_ORDER;   /* ring + lpc[lag][32] */
     e->search_smem_ints = ((size_t)fb_search_smem_words(B) * 4 <= FB_SMEM_BUDGET) ? fb_search_smem_words(B) : 0;
     {
         const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
@@ -147,7 +146,6 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
         free(tab);
         if (ce_ != cudaSuccess) { set_err(err, errlen, "CRC table upload failed", ce_); fb_engine_destroy(e); return nullptr; }
     }
-    cudaFuncSetAttribute(k_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, e->lpc_smem_doubles * 8);
     cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
     cudaFuncSetAttribute(k_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
     cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, e->pack_smem_words * 4);
@@ -222,9 +220,18 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     e->launches += 1;
     FB_MARK(2);
     if (cfg.prediction_type == 2) {
-        const int lpc_threads = 32 * ((2 * (cfg.max_order + 1) + 31) / 32);
-        FB_LAUNCH(k_lpc, dim3(grid_subs), dim3(lpc_threads), (size_t)e->lpc_smem_doubles * 8, st,
-                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts);
+        /* a lane pair per subframe; the register ring is sized by the template (lags 0..ML) */
+        const dim3 lpc_grid((grid_subs + FB_LPC_SUBS_PER_CTA - 1) / FB_LPC_SUBS_PER_CTA);
+#define FB_LPC_GO(ML_)                                                                          \
+        FB_LAUNCH(k_lpc<ML_>, lpc_grid, dim3(FB_LPC_THREADS), 0, st,                              \
+                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts)
+        if (cfg.max_order <= 4) FB_LPC_GO(4);
+        else if (cfg.max_order <= 8) FB_LPC_GO(8);
+        else if (cfg.max_order <= 12) FB_LPC_GO(12);
+        else if (cfg.max_order <= 16) FB_LPC_GO(16);
+        else if (cfg.max_order <= 24) FB_LPC_GO(24);
+        else FB_LPC_GO(32);
+#undef FB_LPC_GO
         e->launches += 1;
     }
     FB_MARK(3);

@@ -1,22 +1,39 @@
 /*
- * k_lpc.cuh -- FP64 LPC analysis, one CTA per subframe (lpc.c):
+ * k_lpc.cuh -- FP64 LPC analysis (lpc.c):
  *   window (lpc.c:28-40) -> autocorrelation (lpc.c:46-71) ->
  *   Levinson-Durbin (lpc.c:77-117) or Schur order estimate (lpc.c:125-162) ->
  *   15-bit quantisation with error feedback (lpc.c:167-219).
  *
  * Bit-exactness rules: every FP64 operation is an
  * individually rounded IEEE op (__dmul_rn/__dadd_rn/..., never contracted to
- * FMA) and every sum is accumulated in the reference's order: one thread owns
- * one (lag, accumulator) chain and walks it sequentially; parallelism comes
- * from lags x accumulators x subframes, not from splitting a sum.
+ * FMA) and every sum is accumulated in the reference's order.  The reference
+ * keeps TWO accumulators per lag (temp over the odd tail terms, temp2 over the
+ * even ones, lpc.c:57-68), so a subframe offers exactly two independent
+ * strictly-ordered walks over the samples, each carrying lag+1 sums.
+ *
+ * Work decomposition: a LANE PAIR per subframe.  Lane `ca` of the pair owns
+ * accumulator `ca` of every lag: lag+1 independent add chains per thread (the
+ * instruction-level parallelism that hides the FP64 latency), fed from a
+ * register ring of the last lag+1 windowed samples.  Per step a lane windows
+ * ONE sample (its own position) and receives its partner's through one
+ * shuffle -- the windowed signal never touches memory.  The int32 planes are
+ * staged through shared memory a tile at a time by the whole warp (coalesced
+ * row loads, conflict-free row stride), so a warp = 16 subframes in lockstep.
+ * Shared-memory traffic per sample-step is one 32-bit load per lane, against
+ * the 2 x 64-bit loads per multiply-add of a thread-per-chain layout.
  */
 #ifndef FLAKE_B200_K_LPC_CUH
 #define FLAKE_B200_K_LPC_CUH
 
 #include "dev_common.cuh"
 
-#define FB_LPC_THREADS 96      /* launch bound; actual block = 32 * ceil(2*(lag+1)/32) */
 #define FB_MAX_ORDER 32
+#ifndef FB_LPC_WARPS
+#define FB_LPC_WARPS 2                                  /* warps per CTA */
+#endif
+#define FB_LPC_THREADS (32 * FB_LPC_WARPS)
+#define FB_LPC_SUBS_PER_CTA (16 * FB_LPC_WARPS)         /* a warp owns 16 subframes */
+#define FB_LPC_ROW 34                                    /* staged row stride in words, == 2 (mod 32) */
 
 /* x86-64 cvttsd2si semantics of the reference's `int q = double` */
 __device__ __forceinline__ int32_t fb_trunc_to_int(double x)
@@ -25,251 +42,306 @@ __device__ __forceinline__ int32_t fb_trunc_to_int(double x)
     return __double2int_rz(x);
 }
 
-/* lpc.c:77-117; rows 0..max_order-1 of lpc[][] */
-__device__ void fb_levinson(const double *autoc, int max_order, const double *refl,
-                            double (*lpc)[FB_MAX_ORDER])
+/* geometry of the register ring for lags 0..ML (ML even) */
+template <int ML> struct FbLpcGeom {
+    static constexpr int K = ML + 2;                     /* ring entries: d[q-ML-1 .. q] */
+    static constexpr int U = K / 2;                      /* steps until the ring indices repeat */
+    static constexpr int R = (2 * U >= 32) ? 1 : 32 / (2 * U);
+    static constexpr int TL = 2 * U * R;                 /* sample positions per staged tile (<= 34) */
+    static constexpr int LD = (TL + 31) / 32;            /* 32-lane loads per staged row */
+};
+
+/* data1[p] of lpc.c:46-56 for a sample value xv at position p (xv == 0 for p >= n).  The
+ * window depends only on min(p, n-1-p) (lpc.c:33-39).  Odd n: the centre sample is
+ * uninitialised in the reference; defined as 0.0 here (parity-exempt). */
+__device__ __forceinline__ double fb_windowed(int32_t xv, int p, int n, double cc)
 {
-    double a[FB_MAX_ORDER];
-    for (int i = 0; i < FB_MAX_ORDER; i++) a[i] = 0.0;
-    double err = autoc ? autoc[0] : 1.0;
-    for (int i = 0; i < max_order; i++) {
-        double r;
-        if (refl) {
-            r = refl[i];
-        } else {
-            r = -autoc[i + 1];
-            for (int j = 0; j < i; j++)
-                r = __dsub_rn(r, __dmul_rn(a[j], autoc[i - j]));
-            r = __ddiv_rn(r, err);
-            err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
-        }
-        a[i] = r;
-        const int half = i >> 1;
-        int j;
-        for (j = 0; j < half; j++) {
-            const double t = a[j];
-            a[j] = __dadd_rn(a[j], __dmul_rn(r, a[i - 1 - j]));
-            a[i - 1 - j] = __dadd_rn(a[i - 1 - j], __dmul_rn(r, t));
-        }
-        if (i & 1)
-            a[j] = __dadd_rn(a[j], __dmul_rn(a[j], r));
-        for (j = 0; j <= i; j++)
-            lpc[i][j] = -a[j];
-    }
+    const int i = min(p, n - 1 - p);
+    const double d = __dsub_rn(cc, (double)i);
+    const double v = __dmul_rn((double)xv, __dsub_rn(1.0, __dmul_rn(d, d)));
+    return ((n & 1) && p == (n >> 1)) ? 0.0 : v;
 }
 
-/* lpc.c:125-162 */
-__device__ int fb_schur_estimate(const double *autoc, int max_order, double (*lpc)[FB_MAX_ORDER])
-{
-    double g0[FB_MAX_ORDER], g1[FB_MAX_ORDER], refl[FB_MAX_ORDER];
-    for (int i = 0; i < max_order; i++) g0[i] = g1[i] = autoc[i + 1];
-    double e = autoc[0];
-    refl[0] = __ddiv_rn(-g1[0], e);
-    e = __dadd_rn(e, __dmul_rn(g1[0], refl[0]));
-    for (int i = 1; i < max_order; i++) {
-        for (int j = 0; j < max_order - i; j++) {
-            const double g1n = g1[j + 1];
-            g1[j] = __dadd_rn(g1n, __dmul_rn(refl[i - 1], g0[j]));
-            g0[j] = __dadd_rn(__dmul_rn(g1n, refl[i - 1]), g0[j]);
-        }
-        refl[i] = __ddiv_rn(-g1[0], e);
-        e = __dadd_rn(e, __dmul_rn(g1[0], refl[i]));
-    }
-    int est = 1;
-    for (int i = max_order - 1; i >= 0; i--)
-        if (fabs(refl[i]) > 0.10) { est = i + 1; break; }
-    fb_levinson(nullptr, est, refl, lpc);
-    return est;
-}
-
-/* lpc.c:167-219 with precision 15 (encode.c:443) */
-__device__ void fb_quantize(double *in, int order, int32_t *out, int32_t *shift)
+/* lpc.c:167-219 with precision 15 (encode.c:443).  `in` is modified like the reference's
+ * row (the rescale branch).  `order` may differ per lane. */
+template <int ML>
+__device__ __forceinline__ void fb_quantize(double (&in)[ML], int order, int32_t (&out)[ML], int32_t &shift)
 {
     const int32_t qmax = (1 << 14) - 1;
     double cmax = 0.0;
-    for (int i = 0; i < order; i++) {
-        const double d = fabs(in[i]);
-        if (d > cmax) cmax = d;
-    }
+#pragma unroll
+    for (int i = 0; i < ML; i++)
+        if (i < order) { const double d = fabs(in[i]); if (d > cmax) cmax = d; }
     if (__dmul_rn(cmax, 32768.0) < 1.0) {
-        *shift = 0;
-        for (int i = 0; i < order; i++) out[i] = 0;
+        shift = 0;
+#pragma unroll
+        for (int i = 0; i < ML; i++) out[i] = 0;
         return;
     }
     int sh = 15;
     while (__dmul_rn(cmax, (double)(1 << sh)) > (double)qmax && sh > 0) sh--;
     if (sh == 0 && cmax > (double)qmax) {
         const double scale = __ddiv_rn((double)qmax, cmax);
-        for (int i = 0; i < order; i++) in[i] = __dmul_rn(in[i], scale);
+#pragma unroll
+        for (int i = 0; i < ML; i++) if (i < order) in[i] = __dmul_rn(in[i], scale);
     }
     double err = 0.0;
     const double mul = (double)(1 << sh);
-    for (int i = 0; i < order; i++) {
-        err = __dadd_rn(err, __dmul_rn(in[i], mul));
-        int32_t q = fb_trunc_to_int(__dadd_rn(err, 0.5));
-        if (q <= -qmax) q = -qmax + 1;
-        if (q > qmax) q = qmax;
-        err = __dsub_rn(err, (double)q);
-        out[i] = q;
+#pragma unroll
+    for (int i = 0; i < ML; i++) {
+        out[i] = 0;
+        if (i < order) {
+            err = __dadd_rn(err, __dmul_rn(in[i], mul));
+            int32_t q = fb_trunc_to_int(__dadd_rn(err, 0.5));
+            if (q <= -qmax) q = -qmax + 1;
+            if (q > qmax) q = qmax;
+            err = __dsub_rn(err, (double)q);
+            out[i] = q;
+        }
     }
-    *shift = sh;
+    shift = sh;
 }
 
-#define FB_LPC_CHUNK 512          /* window samples produced per round */
-#define FB_LPC_HIST  32           /* samples of the previous round kept in front (>= max lag) */
-#define FB_LPC_BUF   (FB_LPC_HIST + FB_LPC_CHUNK)
-#define FB_LPC_RING  (2 * FB_LPC_BUF)   /* two buffers, alternating */
-
-/* data1[p] of lpc.c:46-56: windowed sample p, 0 at p == n.  The window value depends
- * only on min(p, n-1-p) (lpc.c:33-39), so it is recomputed per position instead of being
- * kept for the mirrored sample.  Odd n: the centre sample is uninitialised in the
- * reference; defined as 0.0 here (parity-exempt). */
-__device__ __forceinline__ double fb_windowed(const int32_t *__restrict__ x, int p, int n, int half, double cc)
+/* one Levinson step (lpc.c:92-111): order index i, reflection/prediction coefficient r */
+template <int ML>
+__device__ __forceinline__ void fb_levinson_update(double (&a)[ML], int i, double r)
 {
-    if (p >= n || ((n & 1) && p == half)) return 0.0;
-    const int i = p < half ? p : n - 1 - p;
-    const double d = __dsub_rn(cc, (double)i);
-    const double win = __dsub_rn(1.0, __dmul_rn(d, d));
-    return __dmul_rn((double)x[p], win);
+    const int half = i >> 1;
+    a[i] = r;
+#pragma unroll
+    for (int j = 0; j < ML / 2; j++) {
+        if (j < half) {
+            const double t = a[j];
+            a[j] = __dadd_rn(a[j], __dmul_rn(r, a[i - 1 - j]));
+            a[i - 1 - j] = __dadd_rn(a[i - 1 - j], __dmul_rn(r, t));
+        }
+    }
+    if (i & 1) a[half] = __dadd_rn(a[half], __dmul_rn(a[half], r));
+}
+
+template <int ML>
+__device__ __forceinline__ void fb_store_row(int32_t *co, int32_t *so, int rowi, const int32_t (&q)[ML], int32_t sh)
+{
+#pragma unroll
+    for (int j = 0; j < ML; j++)
+        if (j <= rowi) co[rowi * FB_MAX_ORDER + j] = q[j];
+    so[rowi] = sh;
 }
 
 /*
- * coefs_out: [subframe][32][32] int32, shift_out: [subframe][32].
- * Block = 32 * ceil(2*(lag+1)/32) threads: thread ch owns chain (lag ch>>1, accumulator ch&1)
- * of lpc.c:57-68 -- one warp per subframe up to order 15.
- *
- * The chains of all lags advance in lockstep over the sample index, so only a sliding
- * window of the windowed signal is live: it is produced 512 samples at a time into a
- * 1024-entry shared ring (8 KB) straight from the int32 plane, whatever the block size.
- * Dynamic shared memory: ring[1024] doubles, then lpc[lag][32] doubles.
+ * coefs_out: [subframe][32][32] int32 (row = order-1, entries 0..order-1 written),
+ * shift_out: [subframe][32].  Grid: ceil(subframes / FB_LPC_SUBS_PER_CTA) CTAs.
  */
+template <int ML>
 __global__ void __launch_bounds__(FB_LPC_THREADS)
 k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
       FbSub *subs, int32_t *coefs_out, int32_t *shift_out)
 {
-    FB_DYN_SMEM(dyn);
-    __shared__ double s_autoc[2 * (FB_MAX_ORDER + 1)];
-    __shared__ int s_est;
-    double *ring = reinterpret_cast<double *>(dyn);
-    double (*s_lpc)[FB_MAX_ORDER] = reinterpret_cast<double (*)[FB_MAX_ORDER]>(ring + FB_LPC_RING);
+    typedef FbLpcGeom<ML> G;
+    __shared__ int32_t s_rows[FB_LPC_WARPS][2][16 * FB_LPC_ROW];
+    __shared__ const int32_t *s_ptr[FB_LPC_WARPS][16];
+    __shared__ int s_n[FB_LPC_WARPS][16];
 
-    const int C = cfg.channels;
-    const uint32_t sf = blockIdx.x;
-    const uint32_t f = sf / (uint32_t)C;
-    const int c = (int)(sf % (uint32_t)C);
-    if (f >= *nframes) return;
-    const FbFrame fr = frames[f];
-    const int n = (int)fr.n;
-    FbSub *sb = &subs[sf];
-    const int lag = cfg.max_order;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ca = lane & 1, row = lane >> 1;
+    const int C = cfg.channels, lag = cfg.max_order;
+    const uint32_t nsubs = *nframes * (uint32_t)C;
+    const uint32_t sf = blockIdx.x * FB_LPC_SUBS_PER_CTA + (uint32_t)(warp * 16 + row);
+
     /* same gate as optimize.c:143-193: only the LPC branch needs coefficients */
-    if (sb->is_const || n < 5 || cfg.prediction_type != 2 || n <= lag) return;
+    int n = 0;
+    const int32_t *x = smp;
+    FbSub *sb = nullptr;
+    if (sf < nsubs) {
+        const uint32_t f = sf / (uint32_t)C;
+        const int c = (int)(sf % (uint32_t)C);
+        const FbFrame fr = frames[f];
+        sb = &subs[sf];
+        if (!(sb->is_const || fr.n < 5u || cfg.prediction_type != 2 || (int)fr.n <= lag)) {
+            n = (int)fr.n;
+            x = smp + (size_t)fr.start * C + (size_t)c * n;
+        }
+    }
+    const int nmax = (int)__reduce_max_sync(FB_FULL_MASK, (unsigned)n);
+    if (nmax == 0) return;                               /* warp-uniform */
+    if (ca == 0) { s_ptr[warp][row] = x; s_n[warp][row] = n; }
+    __syncwarp();
 
-    const int32_t *__restrict__ x = smp + (size_t)fr.start * C + (size_t)c * n;
-    const int tid = threadIdx.x, T = blockDim.x;
     const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
-    const int half = n >> 1;
 
-    /* chain state */
-    const bool active = tid < 2 * (lag + 1);
-    const int ci = tid >> 1, ca = tid & 1;
-    double s = 1.0;                               /* lpc.c:58-59: both accumulators start at 1.0 */
-    int j = lag + 1 + ca;                         /* next tail term of this chain */
-    const int last = n - 1;
+    /* ---- head terms (lpc.c:60-61): both lanes compute them, lane 1 starts over at 1.0 ---- */
+    double acc[ML + 1];
+    {
+        double d0[ML + 1];
+#pragma unroll
+        for (int p = 0; p <= ML; p++) d0[p] = fb_windowed(p < n ? x[p] : 0, p, n, cc);
+#pragma unroll
+        for (int i = 0; i <= ML; i++) {
+            double s = 1.0;
+#pragma unroll
+            for (int j = 0; j <= ML - i; j++)
+                if (j <= lag - i) s = __dadd_rn(s, __dmul_rn(d0[j + i], d0[j]));
+            acc[i] = ca ? 1.0 : s;
+        }
+    }
 
-    int which = 0;
-    for (int base = 0; base <= n; base += FB_LPC_CHUNK, which ^= 1) {
-        double *buf = ring + which * FB_LPC_BUF;              /* buf[FB_LPC_HIST + (p - base)] = data1[p] */
-        const double *prev = ring + (which ^ 1) * FB_LPC_BUF;
-        const int end = min(base + FB_LPC_CHUNK, n + 1);      /* positions [base, end) */
-        /* produce: plane loads first (independent), then the FP64 window arithmetic */
-        for (int p0 = base + tid; p0 < end; p0 += 8 * T) {
-            int32_t xv[8];
+    /* ---- ring of the windowed samples in front of the first tail term ------------------
+     * Lane ca walks q = lag+1+ca, +2, ...; before a step the ring holds d[q-2-k] at logical
+     * k.  Lane 0 uses its partner's value one step late (d[q-1] was the partner's previous
+     * position), lane 1 uses it at once. */
+    double D[G::K];
 #pragma unroll
-            for (int q = 0; q < 8; q++) { const int p = p0 + q * T; xv[q] = p < n ? x[p] : 0; }
+    for (int k = 0; k < G::K; k++) {
+        const int p = lag - 1 - k + ca;
+        D[k] = fb_windowed((p >= 0 && p < n) ? x[p] : 0, p, n, cc);
+    }
+    double other_prev = fb_windowed(lag < n ? x[lag] : 0, lag, n, cc);
+
+    const int P0 = lag + 1;
+    const int ntiles = (nmax - P0 + G::TL - 1) / G::TL;
+    int32_t pre[16 * G::LD];
+    int32_t *rows0 = s_rows[warp][0], *rows1 = s_rows[warp][1];
+
+#define FB_LPC_LOAD_TILE(tb)                                                              \
+    do {                                                                                  \
+        _Pragma("unroll")                                                                 \
+        for (int r = 0; r < 16; r++) {                                                    \
+            const int32_t *rp = s_ptr[warp][r];                                           \
+            const int rn = s_n[warp][r];                                                  \
+            _Pragma("unroll")                                                             \
+            for (int l = 0; l < G::LD; l++) {                                             \
+                const int p = (tb) + lane + 32 * l;                                       \
+                pre[r * G::LD + l] = (lane + 32 * l < G::TL && p < rn) ? rp[p] : 0;       \
+            }                                                                             \
+        }                                                                                 \
+    } while (0)
+#define FB_LPC_STORE_TILE(dst)                                                            \
+    do {                                                                                  \
+        _Pragma("unroll")                                                                 \
+        for (int r = 0; r < 16; r++) {                                                    \
+            _Pragma("unroll")                                                             \
+            for (int l = 0; l < G::LD; l++)                                               \
+                if (lane + 32 * l < G::TL) (dst)[r * FB_LPC_ROW + lane + 32 * l] = pre[r * G::LD + l]; \
+        }                                                                                 \
+    } while (0)
+
+    if (ntiles > 0) {
+        FB_LPC_LOAD_TILE(P0);
+        FB_LPC_STORE_TILE(rows0);
+    }
+    __syncwarp();
+    for (int t = 0; t < ntiles; t++) {
+        const int tb = P0 + t * G::TL;
+        const int32_t *cur = (t & 1) ? rows1 : rows0;
+        int32_t *nxt = (t & 1) ? rows0 : rows1;
+        if (t + 1 < ntiles) FB_LPC_LOAD_TILE(tb + G::TL);          /* in flight during the tile */
+        const int32_t *mine = cur + row * FB_LPC_ROW + ca;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int p = p0 + q * T;
-                if (p < end) {
-                    double v = 0.0;
-                    if (p < n && !((n & 1) && p == half)) {
-                        const int i = p < half ? p : n - 1 - p;
-                        const double d = __dsub_rn(cc, (double)i);
-                        v = __dmul_rn((double)xv[q], __dsub_rn(1.0, __dmul_rn(d, d)));
-                    }
-                    buf[FB_LPC_HIST + (p - base)] = v;
-                }
+        for (int b = 0; b < G::R; b++) {
+#pragma unroll
+            for (int u = 0; u < G::U; u++) {
+                const int off = b * 2 * G::U + 2 * u;
+                const double own = fb_windowed(mine[off], tb + off + ca, n, cc);
+                const double other = __shfl_xor_sync(FB_FULL_MASK, own, 1);
+                const int pos0 = G::K - 2 - 2 * u;                  /* physical slot of logical 0 */
+                D[pos0] = own;
+                D[pos0 + 1] = ca ? other : other_prev;
+                other_prev = other;
+#pragma unroll
+                for (int i = 0; i <= ML; i++)
+                    acc[i] = __dadd_rn(acc[i], __dmul_rn(own, D[(pos0 + i) % G::K]));
             }
         }
-        if (tid < FB_LPC_HIST)                                  /* carry the last 32 samples over */
-            buf[tid] = base ? prev[FB_LPC_CHUNK + tid] : 0.0;
-        __syncthreads();
-        if (active) {
-            const double *w = buf + FB_LPC_HIST - base;          /* w[p] = data1[p], p >= base - 32 */
-            if (base == 0 && ca == 0)                            /* head terms, lpc.c:60-61 */
-                for (int q = 0; q <= lag - ci; q++)
-                    s = __dadd_rn(s, __dmul_rn(w[q + ci], w[q]));
-            const int lim = min(end - 1, last);
-            /* tail terms in order; the products do not depend on the running sum, so the
-             * loads and multiplies of the next 8 terms are issued while the strictly
-             * ordered add chain of the current 8 drains */
-            if (j + 14 <= lim) {
-                const double *pu = w + j, *pv = w + j - ci;
-                double u0[8], v0[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) { u0[q] = pu[2 * q]; v0[q] = pv[2 * q]; }
-                while (j + 30 <= lim) {
-                    pu += 16; pv += 16;
-                    double u1[8], v1[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) { u1[q] = pu[2 * q]; v1[q] = pv[2 * q]; }
-                    double pr[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) pr[q] = __dmul_rn(u0[q], v0[q]);
-#pragma unroll
-                    for (int q = 0; q < 8; q++) s = __dadd_rn(s, pr[q]);
-#pragma unroll
-                    for (int q = 0; q < 8; q++) { u0[q] = u1[q]; v0[q] = v1[q]; }
-                    j += 16;
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++) s = __dadd_rn(s, __dmul_rn(u0[q], v0[q]));
-                j += 16;
-            }
-            for (; j <= lim; j += 2)
-                s = __dadd_rn(s, __dmul_rn(w[j], w[j - ci]));
-        }
-        __syncthreads();
+        if (t + 1 < ntiles) FB_LPC_STORE_TILE(nxt);
+        __syncwarp();
     }
-    if (active) s_autoc[tid] = s;
-    __syncthreads();
-    /* fold the two accumulators (autoc[i] = temp + temp2) in place */
-    if (tid == 0)
-        for (int i = 0; i <= lag; i++)
-            s_autoc[i] = __dadd_rn(s_autoc[2 * i], s_autoc[2 * i + 1]);
-    __syncthreads();
+#undef FB_LPC_LOAD_TILE
+#undef FB_LPC_STORE_TILE
 
-    const int om = cfg.order_method;
-    if (tid == 0) {
-        int est = lag;
-        if (om == 1) est = fb_schur_estimate(s_autoc, lag, s_lpc);
-        else fb_levinson(s_autoc, lag, nullptr, s_lpc);
-        s_est = est;
-        sb->est_order = est;
-    }
-    __syncthreads();
+    /* autoc[i] = temp + temp2 (lpc.c:67) */
+    double autoc[ML + 1];
+#pragma unroll
+    for (int i = 0; i <= ML; i++)
+        autoc[i] = __dadd_rn(acc[i], __shfl_xor_sync(FB_FULL_MASK, acc[i], 1));
 
+    if (n == 0) return;
+    const bool writer = ca == 0;
     int32_t *co = coefs_out + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
     int32_t *so = shift_out + (size_t)sf * FB_MAX_ORDER;
-    if (om == 0 || om == 1) {
-        if (tid == 0) {
-            const int i = s_est - 1;
-            fb_quantize(s_lpc[i], i + 1, co + i * FB_MAX_ORDER, so + i);
+    const int om = cfg.order_method;
+    double a[ML];
+#pragma unroll
+    for (int i = 0; i < ML; i++) a[i] = 0.0;
+
+    if (om == 1) {
+        /* Schur recursion and order estimate, lpc.c:125-154 */
+        double g0[ML], g1[ML], refl[ML];
+#pragma unroll
+        for (int i = 0; i < ML; i++) { g0[i] = g1[i] = autoc[i + 1]; refl[i] = 0.0; }
+        double e = autoc[0];
+        refl[0] = __ddiv_rn(-g1[0], e);
+        e = __dadd_rn(e, __dmul_rn(g1[0], refl[0]));
+#pragma unroll
+        for (int i = 1; i < ML; i++) {
+            if (i < lag) {
+#pragma unroll
+                for (int j = 0; j < ML - i; j++) {
+                    if (j < lag - i) {
+                        const double g1n = g1[j + 1];
+                        g1[j] = __dadd_rn(g1n, __dmul_rn(refl[i - 1], g0[j]));
+                        g0[j] = __dadd_rn(__dmul_rn(g1n, refl[i - 1]), g0[j]);
+                    }
+                }
+                refl[i] = __ddiv_rn(-g1[0], e);
+                e = __dadd_rn(e, __dmul_rn(g1[0], refl[i]));
+            }
         }
-    } else {
-        for (int i = tid; i < lag; i += T)
-            fb_quantize(s_lpc[i], i + 1, co + i * FB_MAX_ORDER, so + i);
+        int est = 1;
+#pragma unroll
+        for (int i = 0; i < ML; i++)
+            if (i < lag && fabs(refl[i]) > 0.10) est = i + 1;           /* highest such i */
+        /* Levinson from the reflection coefficients up to the estimate, lpc.c:156 */
+#pragma unroll
+        for (int i = 0; i < ML; i++)
+            if (i < est) fb_levinson_update<ML>(a, i, refl[i]);
+        double rowv[ML];
+        int32_t q[ML], sh;
+#pragma unroll
+        for (int j = 0; j < ML; j++) rowv[j] = -a[j];
+        fb_quantize<ML>(rowv, est, q, sh);
+        if (writer) {
+#pragma unroll
+            for (int j = 0; j < ML; j++)
+                if (j < est) co[(est - 1) * FB_MAX_ORDER + j] = q[j];
+            so[est - 1] = sh;
+            sb->est_order = est;
+        }
+        return;
     }
+
+    /* Levinson-Durbin, lpc.c:77-117; rows are quantised as they appear */
+    double err = autoc[0];
+#pragma unroll
+    for (int i = 0; i < ML; i++) {
+        if (i < lag) {
+            double r = -autoc[i + 1];
+#pragma unroll
+            for (int j = 0; j < i; j++)
+                r = __dsub_rn(r, __dmul_rn(a[j], autoc[i - j]));
+            r = __ddiv_rn(r, err);
+            err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
+            fb_levinson_update<ML>(a, i, r);
+            if (om >= 2 || i == lag - 1) {
+                double rowv[ML];
+                int32_t q[ML], sh;
+#pragma unroll
+                for (int j = 0; j < ML; j++) rowv[j] = j <= i ? -a[j] : 0.0;
+                fb_quantize<ML>(rowv, i + 1, q, sh);
+                if (writer) fb_store_row<ML>(co, so, i, q, sh);
+            }
+        }
+    }
+    if (writer) sb->est_order = lag;
 }
 
 #endif

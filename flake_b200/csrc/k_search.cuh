@@ -16,7 +16,9 @@
 #include "dev_common.cuh"
 #include "k_lpc.cuh"
 
-#define FB_SEARCH_THREADS 32     /* one warp per subframe: no CTA-wide barriers on the hot loop */
+#ifndef FB_SEARCH_THREADS
+#define FB_SEARCH_THREADS 64     /* 16 samples per thread and tile; measured best of 32/64/128/256 on B200 */
+#endif
 
 struct FbSearchShared {
     unsigned long long sums[512];   /* level L lives at [(1<<L)-1, (1<<(L+1))-1) */

@@ -354,6 +354,12 @@ extern "C" float fb_cuda_event_elapsed_ms(void *a, void *b)
     return ms;
 }
 extern "C" int fb_cuda_device_count(void) { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; }
+extern "C" int fb_cuda_sm_count(int device)
+{
+    int n = 0;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return 0;
+    return cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess ? n : 0;
+}
 extern "C" int fb_cuda_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -1; }
 
 #ifdef FLAKE_B200_CUDA_EMU

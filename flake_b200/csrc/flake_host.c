@@ -25,7 +25,8 @@
 #include <time.h>
 
 #define FB_VERSION "SVN"
-#define FB_DEFAULT_CHUNK_BLOCKS 2048
+#define FB_FALLBACK_CHUNK_BLOCKS 2048
+#define FB_CHUNK_TARGET_INTS (80u << 20)      /* channel-samples per chunk the default aims for */
 
 typedef struct FbLane {
     void *h_in, *d_in;              /* pinned staging + device copy of the chunk's PCM */
@@ -64,6 +65,8 @@ typedef struct FbCtx {
 } FbCtx;
 
 static int g_device = -2;           /* -2: not chosen yet */
+struct FbCtx;
+static int default_chunk_blocks(const struct FbCtx *c, unsigned int stream_samples);
 
 static double now_ms(void)
 {
@@ -522,9 +525,7 @@ int flake_encode_init(FlakeContext *s)
         g_device = env ? atoi(env) : -1;
     }
     c->device = g_device;
-    const char *cb = getenv("FLAKE_B200_CHUNK_BLOCKS");
-    c->chunk_blocks = cb ? atoi(cb) : FB_DEFAULT_CHUNK_BLOCKS;
-    if (c->chunk_blocks < 1) c->chunk_blocks = FB_DEFAULT_CHUNK_BLOCKS;
+    c->chunk_blocks = default_chunk_blocks(c, s->samples);
     c->eng1 = fb_engine_create(g, c->device, 1, c->err, sizeof c->err);
     if (!c->eng1) {
         fprintf(stderr, "flake_b200: cannot create the CUDA engine: %s\n", c->err);
@@ -648,6 +649,30 @@ static void *md5_worker(void *arg)
         pthread_mutex_unlock(&p->mu);
     }
     return NULL;
+}
+
+/*
+ * Blocks per engine pass.  Every kernel's grid is a multiple of the block count, so the
+ * default is a multiple of the device's SM count (B200: 148 x 64 = 9472 blocks of 4096 stereo
+ * samples, about 80 M channel-samples): whole waves for the per-subframe grids and two lane
+ * pairs' worth of warps per scheduler for k_lpc.  Streams shorter than that get an engine of
+ * their own size.  FLAKE_B200_CHUNK_BLOCKS overrides.
+ */
+static int default_chunk_blocks(const FbCtx *c, unsigned int stream_samples)
+{
+    const char *cb = getenv("FLAKE_B200_CHUNK_BLOCKS");
+    if (cb && atoi(cb) >= 1) return atoi(cb);
+    const uint64_t per_block = (uint64_t)c->params.block_size * (uint64_t)c->channels;
+    const int sms = fb_cuda_sm_count(c->device);
+    uint64_t blocks = FB_CHUNK_TARGET_INTS / (per_block ? per_block : 1);
+    if (sms > 0 && blocks >= (uint64_t)sms) blocks -= blocks % (uint64_t)sms;
+    if (blocks < 1) blocks = 1;
+    if (sms <= 0 && blocks > FB_FALLBACK_CHUNK_BLOCKS) blocks = FB_FALLBACK_CHUNK_BLOCKS;
+    if (stream_samples) {
+        const uint64_t need = ((uint64_t)stream_samples + (uint64_t)c->params.block_size - 1) / (uint64_t)c->params.block_size;
+        if (need < blocks) blocks = need;
+    }
+    return (int)blocks;
 }
 
 int flake_b200_set_chunk_blocks(FlakeContext *s, int blocks)

@@ -7,8 +7,20 @@
  * (rice.c:76-95), the pairwise-summed pyramid (rice.c:96-102), one Rice
  * parameter per partition (rice.c:30-74) and the smallest total over the
  * allowed partition orders with ties going to the HIGHER order (rice.c:128-135).
- * Only the sums leave registers; the residual itself is stored once, for the
- * chosen predictor.
+ *
+ * Shape of one candidate evaluation:
+ *   tiles     every thread owns 16-sample runs; the run and its history come from the
+ *             staged plane with 128-bit shared loads, the residuals stay in registers,
+ *             one zig-zag sum per run goes to shared memory;
+ *   barrier
+ *   finish    warp 0 alone folds the run sums into the partition pyramid with shuffles
+ *             (a lane holds 1..8 partitions of the finest level, then pairs merge),
+ *             picks parameter and partition order, posts the total;
+ *   barrier
+ * All candidate coefficient rows are staged once per subframe, so nothing else
+ * separates two candidates.  The Rice parameters of the best candidate so far are
+ * kept beside the search, which makes the last pass (optimize.c:266-275) a pure
+ * residual store.
  */
 #ifndef FLAKE_B200_K_SEARCH_CUH
 #define FLAKE_B200_K_SEARCH_CUH
@@ -20,16 +32,18 @@
 #define FB_SEARCH_THREADS 64     /* 16 samples per thread and tile; measured best of 32/64/128/256 on B200 */
 #endif
 
+template <int MAXP>
 struct FbSearchShared {
-    unsigned long long sums[512];   /* level L lives at [(1<<L)-1, (1<<(L+1))-1) */
-    uint8_t  kbuf[512];
-    uint32_t lvl_bits[9];
-    uint32_t lvl_rice2[9];
-    int32_t  coef[FB_MAX_ORDER];
-    int32_t  shift;
+    unsigned long long sums[256];   /* finest-level partition sums when runs do not tile the partitions */
+    uint8_t  kbuf[512];             /* candidate: parameter of partition j at level L at [(1<<L)-1+j] */
+    uint8_t  kbest[256];            /* best candidate so far: parameters at its partition order */
+    int32_t  coef[MAXP][MAXP];      /* candidate rows (row = order-1), zero padded */
+    int32_t  shift[MAXP];
+    uint32_t sumabs[MAXP];          /* sum |coef| per row */
     uint32_t result;
-    int32_t  best_porder;
-    int32_t  best_method;
+    int32_t  porder, method;        /* of the candidate just finished */
+    int32_t  best_porder, best_method;
+    uint32_t best_bits;
 };
 
 /* optimize.c:34-68, one sample */
@@ -56,72 +70,127 @@ __device__ __forceinline__ int32_t fb_lpc_residual(const int32_t *x, int i, int 
 }
 
 /* ------------------------------------------------------------------ */
-/* candidate costing                                                    */
+/* finish: partition pyramid, Rice parameters, best partition order     */
 /* ------------------------------------------------------------------ */
-/* partition-order limits of a candidate (rice.c:148-171).  The finest-level sums and
- * the per-level accumulators are zero on entry: the kernel zeroes them once and
- * fb_eval_finish re-zeroes what it consumed. */
-__device__ __forceinline__ void fb_eval_begin(FbSearchShared &S, int n, int order, int pmin_cfg,
-                                              int pmax_cfg, int &pmin, int &pmax)
+/*
+ * Warp 0 only.  Finest-level sums come from `runsum` (one per 16-sample run, `per` runs per
+ * partition) or, when runsum == NULL, from S.sums.  The pairwise pyramid of rice.c:96-102 is
+ * exact integer addition, so the order of summation is free.  Levels are visited from the
+ * finest down and a level replaces the best only when strictly smaller, which is the
+ * reference's ascending scan with `<=` (ties to the higher order, rice.c:128-135).
+ * Posts S.result (rice.c:157-187 total), S.porder, S.method and the parameters in S.kbuf.
+ */
+template <int MAXP>
+__device__ __forceinline__ void fb_finish_warp0(FbSearchShared<MAXP> &S, const unsigned long long *runsum,
+                                                int per, int n, int is_lpc, int order, int obits,
+                                                int pmin, int pmax)
 {
-    pmin = fb_limit_porder(pmin_cfg, n, order);
-    pmax = fb_limit_porder(pmax_cfg, n, order);
-}
-
-/* Partition sums of every allowed level straight from the finest level (the
- * pairwise pyramid of rice.c:96-102 is exact integer addition, so the order of
- * summation is free), per-partition Rice parameter (rice.c:47-74), best partition
- * order with ties to the higher one (rice.c:128-135), total (rice.c:157-171). */
-__device__ __forceinline__ uint32_t fb_eval_finish(FbSearchShared &S, int n, int is_lpc, int order,
-                                                   int obits, int pmin, int pmax, FbSub *store)
-{
-    const int tid = threadIdx.x, T = blockDim.x;
-    const int nparts = 1 << pmax;
-    const unsigned long long *fine = &S.sums[nparts - 1];
-    __syncthreads();                                   /* finest sums complete */
-    const int e_first = (1 << pmin) - 1, e_end = (1 << (pmax + 1)) - 1;
-    for (int e = e_first + tid; e < e_end; e += T) {
-        const int L = fb_ilog2((uint32_t)(e + 1));
-        const int j = e - ((1 << L) - 1);
-        const int span = 1 << (pmax - L);
-        unsigned long long sum = 0;
-        for (int q = 0; q < span; q++) sum += fine[j * span + q];
-        const int cnt = (n >> L) - (j == 0 ? order : 0);
-        const int k = fb_rice_k(sum, cnt);
-        S.kbuf[e] = (uint8_t)k;
-        atomicAdd(&S.lvl_bits[L], (uint32_t)fb_rice_count64(sum, cnt, k));
-        if (k > 14) atomicOr(&S.lvl_rice2[L], 1u);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t best = 0xffffffffu;
-        int bl = pmin;
-        for (int L = pmin; L <= pmax; L++) {
-            const uint32_t b = S.lvl_bits[L] + 4u * (1u << L);
-            if (b <= best) { best = b; bl = L; }
+    const int lane = threadIdx.x & 31;
+    unsigned long long s[8];
+#pragma unroll
+    for (int v = 0; v < 8; v++) s[v] = 0;
+    if (pmax >= 5) {
+        const int V = 1 << (pmax - 5);
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            if (v < V) {
+                const int p = lane * V + v;
+                if (runsum) {
+                    unsigned long long a = 0;
+                    for (int q = 0; q < per; q++) a += runsum[p * per + q];
+                    s[v] = a;
+                } else {
+                    s[v] = S.sums[p];
+                }
+            }
         }
-        const uint32_t method = S.lvl_rice2[bl];
+    } else {
+        const int g = 32 >> pmax, j = lane / g, sub = lane % g;
+        unsigned long long a = 0;
+        if (runsum) {
+            for (int q = sub; q < per; q += g) a += runsum[j * per + q];
+            for (int o = 1; o < g; o <<= 1) a += __shfl_xor_sync(FB_FULL_MASK, a, o);
+        } else {
+            a = S.sums[j];
+        }
+        s[0] = a;
+    }
+
+    uint32_t best = 0xffffffffu;
+    int bl = pmin, bmethod = 0;
+    for (int L = pmax; L >= pmin; L--) {
+        uint32_t bits = 0;
+        int flag = 0;
+        if (L >= 5) {
+            const int Vc = 1 << (L - 5);
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                if (v < Vc) {
+                    const int j = lane * Vc + v;
+                    const int cnt = (n >> L) - (j == 0 ? order : 0);
+                    const int k = fb_rice_k(s[v], cnt);
+                    S.kbuf[(1 << L) - 1 + j] = (uint8_t)k;
+                    bits += (uint32_t)fb_rice_count64(s[v], cnt, k);
+                    flag |= (k > 14);
+                }
+            }
+        } else {
+            const int g = 32 >> L, j = lane / g;
+            const int cnt = (n >> L) - (j == 0 ? order : 0);
+            const int k = fb_rice_k(s[0], cnt);
+            if ((lane % g) == 0) {
+                S.kbuf[(1 << L) - 1 + j] = (uint8_t)k;
+                bits = (uint32_t)fb_rice_count64(s[0], cnt, k);
+                flag = (k > 14);
+            }
+        }
+        const uint32_t lvl = __reduce_add_sync(FB_FULL_MASK, bits);
+        const int r2 = __any_sync(FB_FULL_MASK, flag) ? 1 : 0;
+        const uint32_t b = lvl + 4u * (1u << L);
+        if (b < best) { best = b; bl = L; bmethod = r2; }
+        if (L > pmin) {
+            if (L > 5) {
+                const int Vh = 1 << (L - 6);
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    if (v < Vh) s[v] = s[2 * v] + s[2 * v + 1];
+            } else {
+                s[0] += __shfl_xor_sync(FB_FULL_MASK, s[0], 1 << (5 - L));
+            }
+        }
+    }
+    if (lane == 0) {
         uint32_t total = (uint32_t)(order * obits + 2);
         if (is_lpc) total += 4u + 5u + (uint32_t)order * 15u;
         total += best;
-        total += method + 4u;
+        total += (uint32_t)bmethod + 4u;
         S.result = total;
-        S.best_porder = bl;
-        S.best_method = (int32_t)method;
-        if (store) { store->porder = bl; store->method = (int32_t)method; store->est_bits = total; }
+        S.porder = bl;
+        S.method = bmethod;
     }
-    __syncthreads();
-    if (store) {
-        const int np = 1 << S.best_porder;
-        for (int j = tid; j < np; j += T) store->params[j] = S.kbuf[np - 1 + j];
+}
+
+/* the candidate just finished is the best so far: warp 0 keeps its parameters */
+template <int MAXP>
+__device__ __forceinline__ void fb_keep_best(FbSearchShared<MAXP> &S, uint32_t bits)
+{
+    if (threadIdx.x < 32) {
+        __syncwarp();
+        const int bl = S.porder, np = 1 << bl;
+        for (int j = threadIdx.x; j < np; j += 32) S.kbest[j] = S.kbuf[np - 1 + j];
+        if (threadIdx.x == 0) { S.best_porder = bl; S.best_method = S.method; S.best_bits = bits; }
+        __syncwarp();
     }
-    const uint32_t result = S.result;
-    /* leave the accumulators zeroed for the next candidate (its first write to them
-     * comes after the barrier that follows the coefficient load) */
-    for (int e = tid; e < nparts; e += T) S.sums[nparts - 1 + e] = 0;
-    if (tid < 9) { S.lvl_bits[tid] = 0; S.lvl_rice2[tid] = 0; }
+}
+
+/* every thread: write the kept decision to the subframe record */
+template <int MAXP>
+__device__ __forceinline__ void fb_store_best(FbSearchShared<MAXP> &S, FbSub *sb)
+{
     __syncthreads();
-    return result;
+    const int np = 1 << S.best_porder;
+    for (int j = threadIdx.x; j < np; j += blockDim.x) sb->params[j] = S.kbest[j];
+    if (threadIdx.x == 0) { sb->porder = S.best_porder; sb->method = S.best_method; sb->est_bits = S.best_bits; }
 }
 
 /*
@@ -129,30 +198,35 @@ __device__ __forceinline__ uint32_t fb_eval_finish(FbSearchShared &S, int n, int
  * pointer (global memory for blocks that do not fit shared memory).
  * Every thread of the CTA calls it and gets the total
  * (calc_rice_params_fixed / _lpc return value, rice.c:157-187).
- * res_out != NULL: also store the residual (warm-up = samples).
- * store   != NULL: also record method / porder / params for the packer.
+ * want_sums: cost the candidate; res_out != NULL: store the residual (warm-up = samples).
  */
-__device__ __noinline__ uint32_t fb_evaluate(FbSearchShared &S, const int32_t *x, int n, int is_lpc, int order,
-                                int obits, int pmin_cfg, int pmax_cfg,
-                                int32_t *res_out, FbSub *store)
+template <int MAXP>
+__device__ __noinline__ uint32_t fb_evaluate(FbSearchShared<MAXP> &S, const int32_t *x, int n, int is_lpc, int order,
+                                             int row, int obits, int pmin_cfg, int pmax_cfg,
+                                             int32_t *res_out, bool want_sums)
 {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
-    int pmin, pmax;
-    fb_eval_begin(S, n, order, pmin_cfg, pmax_cfg, pmin, pmax);
+    const int pmin = fb_limit_porder(pmin_cfg, n, order);
+    const int pmax = fb_limit_porder(pmax_cfg, n, order);
     const int nparts = 1 << pmax, psize = n >> pmax;
-
-    const int shift = S.shift;
+    const int32_t *coef = S.coef[row];
+    const int shift = S.shift[row];
+    if (want_sums) {
+        for (int e = tid; e < nparts; e += T) S.sums[e] = 0;
+        __syncthreads();
+    }
     for (int base = tid - lane; base < n; base += T) {
         const int i = base + lane;
         unsigned long long u = 0;
         if (i < n) {
             int32_t r;
             if (i < order) r = x[i];
-            else r = is_lpc ? fb_lpc_residual(x, i, order, S.coef, shift)
+            else r = is_lpc ? fb_lpc_residual(x, i, order, coef, shift)
                             : fb_fixed_residual(x, i, order);
             if (res_out) res_out[i] = r;
             if (i >= order) u = fb_zigzag(r);
         }
+        if (!want_sums) continue;
         /* partition index, monotone across the warp; idle lanes carry u = 0 */
         int ic = i < order ? order : i;
         if (ic > n - 1) ic = n - 1;
@@ -165,9 +239,13 @@ __device__ __noinline__ uint32_t fb_evaluate(FbSearchShared &S, const int32_t *x
         }
         const int pn = __shfl_down_sync(FB_FULL_MASK, p, 1);
         if ((lane == 31 || pn != p) && u)
-            atomicAdd(&S.sums[nparts - 1 + p], u);
+            atomicAdd(&S.sums[p], u);
     }
-    return fb_eval_finish(S, n, is_lpc, order, obits, pmin, pmax, store);
+    if (!want_sums) return 0;
+    __syncthreads();
+    if (tid < 32) fb_finish_warp0<MAXP>(S, nullptr, 0, n, is_lpc, order, obits, pmin, pmax);
+    __syncthreads();
+    return S.result;
 }
 
 /* ------------------------------------------------------------------ */
@@ -183,6 +261,8 @@ __host__ __device__ __forceinline__ int fb_skew(int logical) { return logical + 
 __host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n + FB_HIST + FB_RUN) + 8 + 1) & ~1; }
 /* staged plane + one 64-bit zig-zag sum per 16-sample run, in 32-bit words */
 __host__ __device__ __forceinline__ int fb_search_smem_words(int n) { return fb_skew_words(n) + 2 * (((n + FB_RUN - 1) / FB_RUN) + 2); }
+/* word offset of logical (16 m + d) relative to that of logical 16 m; d may be negative */
+__host__ __device__ constexpr int fb_skew_delta(int d) { return d + 4 * (d >= 0 ? d / 16 : -((-d + 15) / 16)); }
 
 /*
  * Residual of the samples [i0, i0+16) with a register sliding window.
@@ -190,23 +270,27 @@ __host__ __device__ __forceinline__ int fb_search_smem_words(int n) { return fb_
  * order are zero).  WIDE: 64-bit prediction and sums (always exact);
  * !WIDE: 32-bit, used only when the caller proved nothing can overflow.
  */
-template <int P, bool WIDE>
-__device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t *xs, int n, int order,
-                                                int psize, int nparts, int tile_base,
-                                                int32_t *res_out, unsigned long long *runsum)
+template <int MAXP, int P, bool WIDE>
+__device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int order,
+                                                int row, int psize, int tile_base,
+                                                int32_t *res_out, unsigned long long *runsum, bool want_sums)
 {
     const int tid = threadIdx.x;
     const int i0 = tile_base + tid * FB_RUN;
     if (i0 >= n) return;
     int32_t c[P];
 #pragma unroll
-    for (int j = 0; j < P; j++) c[j] = S.coef[j];
-    const int shift = S.shift;
+    for (int g = 0; g < P / 4; g++) {
+        const int4 v = *reinterpret_cast<const int4 *>(&S.coef[row][4 * g]);
+        c[4 * g] = v.x; c[4 * g + 1] = v.y; c[4 * g + 2] = v.z; c[4 * g + 3] = v.w;
+    }
+    const int shift = S.shift[row];
 
     int32_t w[P + FB_RUN];
+    const int32_t *xr = xs + fb_skew(i0 + FB_HIST);           /* i0 + FB_HIST is a multiple of 16 */
 #pragma unroll
     for (int g = 0; g < (P + FB_RUN) / 4; g++) {
-        const int4 v = *reinterpret_cast<const int4 *>(xs + fb_skew(i0 + FB_HIST - P + 4 * g));
+        const int4 v = *reinterpret_cast<const int4 *>(xr + fb_skew_delta(4 * g - P));
         w[4 * g] = v.x; w[4 * g + 1] = v.y; w[4 * g + 2] = v.z; w[4 * g + 3] = v.w;
     }
 
@@ -214,19 +298,21 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t
     int32_t r[FB_RUN];
 #pragma unroll
     for (int k = 0; k < FB_RUN; k++) {
-        int32_t rv;
         if (WIDE) {
             long long pred = 0;
 #pragma unroll
             for (int j = 0; j < P; j++) pred += (long long)c[j] * (long long)w[P + k - 1 - j];
-            rv = (int32_t)((long long)w[P + k] - (pred >> shift));
+            r[k] = (int32_t)((long long)w[P + k] - (pred >> shift));
         } else {
             int32_t pred = 0;
 #pragma unroll
             for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
-            rv = w[P + k] - (pred >> shift);
+            r[k] = w[P + k] - (pred >> shift);
         }
-        r[k] = (i0 + k < order) ? w[P + k] : rv;      /* warm-up samples pass through */
+    }
+    if (i0 < order) {                                         /* warm-up samples pass through */
+#pragma unroll
+        for (int k = 0; k < FB_RUN; k++) if (i0 + k < order) r[k] = w[P + k];
     }
     if (res_out) {
         int32_t *dst = res_out + i0;
@@ -239,10 +325,11 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t
             for (int k = 0; k < FB_RUN; k++) if (i0 + k < n) dst[k] = r[k];
         }
     }
+    if (!want_sums) return;
 
     /* zig-zag sums (rice.c:76-95).  Partitions that are whole multiples of the run length
      * (the rule for every power-of-two block size): one sum per run, folded into the
-     * partition sums after the tiles -- no atomics on the hot loop. */
+     * partition sums by the finishing warp -- no atomics on the hot loop. */
     if (runsum) {
         unsigned long long acc;
         if (i0 >= order && i0 + FB_RUN <= n) {
@@ -276,7 +363,7 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t
             const int i = i0 + k;
             if (i < order || i >= n) continue;
             if (i >= nb) {
-                if (acc) atomicAdd(&S.sums[nparts - 1 + pcur], acc);
+                if (acc) atomicAdd(&S.sums[pcur], acc);
                 acc = 0; pcur++; nb += psize;
             }
             /* r[] lives in registers: select without dynamic indexing */
@@ -285,80 +372,77 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared &S, const int32_t
             for (int q = 0; q < FB_RUN; q++) rv = (q == k) ? r[q] : rv;
             acc += fb_zigzag(rv);
         }
-        if (acc) atomicAdd(&S.sums[nparts - 1 + pcur], acc);
+        if (acc) atomicAdd(&S.sums[pcur], acc);
     }
 }
 
-template <int P, bool WIDE>
-__device__ __noinline__ void fb_tiles(FbSearchShared &S, const int32_t *xs, int n, int order, int psize,
-                                      int nparts, int32_t *res_out, unsigned long long *runsum)
+template <int MAXP, int P, bool WIDE>
+__device__ __noinline__ void fb_tiles(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int order, int row, int psize,
+                                      int32_t *res_out, unsigned long long *runsum, bool want_sums)
 {
     for (int tile = 0; tile < n; tile += (int)blockDim.x * FB_RUN)
-        fb_run_residual<P, WIDE>(S, xs, n, order, psize, nparts, tile, res_out, runsum);
+        fb_run_residual<MAXP, P, WIDE>(S, xs, n, order, row, psize, tile, res_out, runsum, want_sums);
 }
 
 /*
- * Fast evaluation.  S.coef holds the coefficients zero-padded to 32 and S.shift
- * the shift (fixed predictors: binomial coefficients, shift 0).  `maxabs`
- * bounds |sample| and decides whether 32-bit arithmetic is provably exact:
+ * Fast evaluation of the candidate in row `row` of S.coef (fixed predictors: binomial
+ * coefficients, shift 0).  `maxabs` bounds |sample| and decides whether 32-bit
+ * arithmetic is provably exact:
  *   |pred| <= sum|c| * maxabs < 2^31, and
  *   |residual| <= maxabs + (sum|c|*maxabs >> shift) + 1 < 2^26 so that a run's
  *   zig-zag sum fits 32 bits.
  */
 template <int MAXP>
-__device__ uint32_t fb_evaluate_fast(FbSearchShared &S, const int32_t *xs, int n, int is_lpc, int order,
-                                     int obits, int pmin_cfg, int pmax_cfg, uint32_t maxabs,
-                                     int32_t *res_out, FbSub *store)
+__device__ __noinline__ uint32_t fb_evaluate_fast(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int order,
+                                                  int row, int obits, int pmin_cfg, int pmax_cfg, uint32_t maxabs,
+                                                  int32_t *res_out, bool want_sums)
 {
-    int pmin, pmax;
-    fb_eval_begin(S, n, order, pmin_cfg, pmax_cfg, pmin, pmax);
+    const int pmin = fb_limit_porder(pmin_cfg, n, order);
+    const int pmax = fb_limit_porder(pmax_cfg, n, order);
     const int nparts = 1 << pmax, psize = n >> pmax;
-    unsigned long long sumabs = 0;
-    for (int j = 0; j < order; j++) { const int32_t v = S.coef[j]; sumabs += (unsigned long long)(v < 0 ? -(long long)v : v); }
-    const unsigned long long pm = sumabs * (unsigned long long)maxabs;
+    const unsigned long long pm = (unsigned long long)S.sumabs[row] * (unsigned long long)maxabs;
     const bool narrow = pm < 0x80000000ull &&
-                        ((unsigned long long)maxabs + (pm >> S.shift) + 1ull) < (1ull << 26);
+                        ((unsigned long long)maxabs + (pm >> S.shift[row]) + 1ull) < (1ull << 26);
     const int P = (order + 3) & ~3;
     /* per-run sums are usable when every partition is a whole number of runs */
     unsigned long long *runsum = (psize % FB_RUN) == 0
         ? reinterpret_cast<unsigned long long *>(const_cast<int32_t *>(xs) + fb_skew_words(n)) : nullptr;
-#define FB_CASE(PP)                                                                           \
-    case PP:                                                                                  \
-        if (narrow) fb_tiles<PP, false>(S, xs, n, order, psize, nparts, res_out, runsum);             \
-        else        fb_tiles<PP, true>(S, xs, n, order, psize, nparts, res_out, runsum);              \
+    if (want_sums && !runsum) {
+        for (int e = threadIdx.x; e < nparts; e += blockDim.x) S.sums[e] = 0;
+        __syncthreads();
+    }
+#define FB_CASE(PP)                                                                                         \
+    case PP:                                                                                                \
+        if (narrow) fb_tiles<MAXP, PP, false>(S, xs, n, order, row, psize, res_out, runsum, want_sums);     \
+        else        fb_tiles<MAXP, PP, true>(S, xs, n, order, row, psize, res_out, runsum, want_sums);      \
         break;
     switch (P) {
         case 0:
         FB_CASE(4) FB_CASE(8) FB_CASE(12)
         default:
-            if (MAXP > 12) {
+            if constexpr (MAXP > 12) {
                 switch (P) {
                     FB_CASE(16) FB_CASE(20) FB_CASE(24) FB_CASE(28)
                     default:
-                        if (narrow) fb_tiles<32, false>(S, xs, n, order, psize, nparts, res_out, runsum);
-                        else        fb_tiles<32, true>(S, xs, n, order, psize, nparts, res_out, runsum);
+                        if (narrow) fb_tiles<MAXP, 32, false>(S, xs, n, order, row, psize, res_out, runsum, want_sums);
+                        else        fb_tiles<MAXP, 32, true>(S, xs, n, order, row, psize, res_out, runsum, want_sums);
                         break;
                 }
             }
             break;
     }
 #undef FB_CASE
-    if (runsum) {
-        __syncthreads();
-        const int per = psize / FB_RUN;
-        for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
-            unsigned long long sum = 0;
-            for (int q = 0; q < per; q++) sum += runsum[p * per + q];
-            S.sums[nparts - 1 + p] = sum;
-        }
-    }
-    return fb_eval_finish(S, n, is_lpc, order, obits, pmin, pmax, store);
+    if (!want_sums) return 0;
+    __syncthreads();
+    if (threadIdx.x < 32) fb_finish_warp0<MAXP>(S, runsum, psize / FB_RUN, n, is_lpc, order, obits, pmin, pmax);
+    __syncthreads();
+    return S.result;
 }
 
 /* one candidate through whichever path the block size allows */
-#define FB_EVAL(is_lpc_, order_, res_, store_)                                                      \
-    (fast ? fb_evaluate_fast<MAXP>(S, xs, n, (is_lpc_), (order_), obits, pmin, pmax, maxabs, (res_), (store_)) \
-          : fb_evaluate(S, xg, n, (is_lpc_), (order_), obits, pmin, pmax, (res_), (store_)))
+#define FB_EVAL(is_lpc_, order_, row_, res_, sums_)                                                           \
+    (fast ? fb_evaluate_fast<MAXP>(S, xs, n, (is_lpc_), (order_), (row_), obits, pmin, pmax, maxabs, (res_), (sums_)) \
+          : fb_evaluate<MAXP>(S, xg, n, (is_lpc_), (order_), (row_), obits, pmin, pmax, (res_), (sums_)))
 
 template <int MAXP>
 __global__ void __launch_bounds__(FB_SEARCH_THREADS)
@@ -366,7 +450,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
          int32_t *res, FbSub *subs, const int32_t *coefs, const int32_t *shifts, int smem_ints)
 {
     FB_DYN_SMEM(dyn);
-    __shared__ FbSearchShared S;
+    __shared__ __align__(16) FbSearchShared<MAXP> S;
 
     const int C = cfg.channels;
     const uint32_t sf = blockIdx.x;
@@ -405,60 +489,70 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
 #pragma unroll 8
         for (int i = n4 + tid; i < n; i += T) xs[fb_skew(i + FB_HIST)] = xg[i];
         for (int i = n + tid; i < n + FB_RUN; i += T) xs[fb_skew(i + FB_HIST)] = 0;
-        fb_cp_async_wait_all();
     }
-    for (int e = tid; e < 512; e += T) S.sums[e] = 0;
-    if (tid < 9) { S.lvl_bits[tid] = 0; S.lvl_rice2[tid] = 0; }
-    if (tid < FB_MAX_ORDER) S.coef[tid] = 0;
-    if (tid == 0) S.shift = 0;
-    __syncthreads();
 
     const int pmin = cfg.min_porder, pmax = cfg.max_porder;
     int min_order = cfg.min_order, max_order = cfg.max_order;
+    const bool fixed = (cfg.prediction_type == 1 || n <= max_order);
 
-    /* FIXED, optimize.c:168-190: the fixed predictors are LPC with binomial
-     * coefficients and shift 0 (optimize.c:44-66) */
-    if (cfg.prediction_type == 1 || n <= max_order) {
+    /* candidate rows: binomial coefficients (optimize.c:44-66 is LPC with shift 0) or the
+     * quantised rows of k_lpc; sum |c| per row for the 32-bit exactness test */
+    if (fixed) {
+        if (tid < 5) {
+            const int32_t bc[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+            const uint32_t sa[5] = {0, 1, 3, 7, 15};
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.coef[tid][j] = bc[tid][j];
+            S.shift[tid] = 0;
+            S.sumabs[tid] = sa[tid];
+        }
+    } else {
+        const int32_t *co = coefs + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
+        const int32_t *so = shifts + (size_t)sf * FB_MAX_ORDER;
+        for (int e = tid; e < MAXP * MAXP; e += T) {
+            const int rowi = e / MAXP, j = e % MAXP;
+            S.coef[rowi][j] = (rowi < max_order && j <= rowi) ? co[rowi * FB_MAX_ORDER + j] : 0;
+        }
+        for (int rowi = tid; rowi < MAXP; rowi += T) {
+            uint32_t sa = 0;
+            if (rowi < max_order)
+                for (int j = 0; j <= rowi; j++) {
+                    const int32_t v = co[rowi * FB_MAX_ORDER + j];
+                    sa += (uint32_t)(v < 0 ? -v : v);                   /* <= 32 * 16383 */
+                }
+            S.sumabs[rowi] = sa;
+            S.shift[rowi] = rowi < max_order ? so[rowi] : 0;
+        }
+    }
+    if (fast) fb_cp_async_wait_all();
+    __syncthreads();
+
+    /* FIXED, optimize.c:168-190: row = order (row 0 is the all-zero order-0 predictor) */
+    if (fixed) {
         if (max_order > 4) max_order = 4;
         int opt = min_order;
         uint32_t best = 0xffffffffu;
-#define FB_SET_FIXED(order_)                                                                  \
-        do {                                                                                  \
-            __syncthreads();                                                                  \
-            if (tid < 4) {                                                                    \
-                const int o_ = (order_);                                                      \
-                const int32_t bc[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}}; \
-                S.coef[tid] = bc[o_ > 4 ? 4 : o_][tid];                                       \
-            }                                                                                 \
-            __syncthreads();                                                                  \
-        } while (0)
         for (int i = min_order; i <= max_order; i++) {
-            FB_SET_FIXED(i);
-            const uint32_t b = FB_EVAL(0, i, nullptr, nullptr);
-            if (b < best) { best = b; opt = i; }
+            const uint32_t b = FB_EVAL(0, i, i, nullptr, true);
+            if (b < best) { best = b; opt = i; fb_keep_best<MAXP>(S, b); }
         }
-        if (opt > 4) opt = 4;   /* min_order > 4 with a tiny last block: undefined in the reference */
+        if (opt > 4 || best == 0xffffffffu) {   /* min_order > 4 with a tiny last block: undefined in the reference */
+            if (opt > 4) opt = 4;
+            const uint32_t b = FB_EVAL(0, opt, opt, nullptr, true);
+            fb_keep_best<MAXP>(S, b);
+        }
         if (tid == 0) { sb->type = 8; sb->order = opt; }
-        FB_SET_FIXED(opt);
-        FB_EVAL(0, opt, rg, sb);
-#undef FB_SET_FIXED
+        FB_EVAL(0, opt, opt, rg, false);
+        fb_store_best<MAXP>(S, sb);
         return;
     }
 
     /* LPC, optimize.c:193-275 */
-    const int32_t *co = coefs + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
-    const int32_t *so = shifts + (size_t)sf * FB_MAX_ORDER;
     const int om = cfg.order_method;
     int opt_order;                       /* 0-based index while searching */
+    bool have_best = false;
 
-#define FB_EVAL_INDEX(idx, out_bits)                                             \
-    do {                                                                         \
-        __syncthreads();                                                         \
-        if (tid < FB_MAX_ORDER) S.coef[tid] = tid <= (idx) ? co[(idx) * FB_MAX_ORDER + tid] : 0; \
-        if (tid == 0) S.shift = so[(idx)];                                       \
-        __syncthreads();                                                         \
-        (out_bits) = FB_EVAL(1, (idx) + 1, nullptr, nullptr);                    \
-    } while (0)
+#define FB_EVAL_INDEX(idx, out_bits) (out_bits) = FB_EVAL(1, (idx) + 1, (idx), nullptr, true)
 
     if (om == 0) {
         opt_order = max_order - 1;
@@ -473,7 +567,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             if (order < 0) order = 0;
             uint32_t b;
             FB_EVAL_INDEX(order, b);
-            if (b < best) { best = b; opt_order = order; }
+            if (b < best) { best = b; opt_order = order; have_best = true; fb_keep_best<MAXP>(S, b); }
         }
     } else if (om == 5) {
         uint32_t best = 0xffffffffu;
@@ -481,7 +575,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         for (int i = 0; i < max_order; i++) {
             uint32_t b;
             FB_EVAL_INDEX(i, b);
-            if (b < best) { best = b; opt_order = i; }
+            if (b < best) { best = b; opt_order = i; have_best = true; fb_keep_best<MAXP>(S, b); }
         }
     } else {
         /* log search, optimize.c:241-261 */
@@ -494,28 +588,26 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 uint32_t b;
                 FB_EVAL_INDEX(i, b);
                 done |= 1u << i;
-                if (b < best) { best = b; opt_order = i; }
+                if (b < best) { best = b; opt_order = i; have_best = true; fb_keep_best<MAXP>(S, b); }
             }
         }
     }
+#undef FB_EVAL_INDEX
 
-    /* final pass for the chosen order, optimize.c:266-275 */
+    /* final pass for the chosen order, optimize.c:266-275: the costing of a searched order is
+     * already known, only its residual is missing */
     {
         const int idx = opt_order;
-        __syncthreads();
-        if (tid < FB_MAX_ORDER) {
-            const int32_t v = tid <= idx ? co[idx * FB_MAX_ORDER + tid] : 0;
-            S.coef[tid] = v;
-            sb->coefs[tid] = v;
+        if (tid < FB_MAX_ORDER) sb->coefs[tid] = (tid <= idx && tid < MAXP) ? S.coef[idx][tid] : 0;
+        if (tid == 0) { sb->type = 32; sb->order = idx + 1; sb->shift = S.shift[idx]; }
+        if (have_best) {
+            FB_EVAL(1, idx + 1, idx, rg, false);
+        } else {
+            const uint32_t b = FB_EVAL(1, idx + 1, idx, rg, true);
+            fb_keep_best<MAXP>(S, b);
         }
-        if (tid == 0) {
-            S.shift = so[idx];
-            sb->type = 32; sb->order = idx + 1; sb->shift = so[idx];
-        }
-        __syncthreads();
-        FB_EVAL(1, idx + 1, rg, sb);
+        fb_store_best<MAXP>(S, sb);
     }
-#undef FB_EVAL_INDEX
 }
 #undef FB_EVAL
 

@@ -128,10 +128,22 @@ __device__ __forceinline__ uint64_t fb_rice_count64(uint64_t sum, int n, int k)
     return (uint64_t)((int64_t)n * (int64_t)(k + 1)) + ((sum - (uint64_t)(n >> 1)) >> k);
 }
 
-/* rice.c:30-45 -- first strict minimum of the uint32-truncated cost over
- * k = 0..30.  The cost is convex in k while nothing wraps, which gives the
- * closed form: smallest k with ((sum - n/2) >> k) <= 2n;
- * otherwise (huge sums, where the uint32 truncation matters) scan. */
+/* rice.c:30-45 literally: first strict minimum of the uint32-truncated cost over k = 0..30.
+ * Out of line: only sums >= 2^31 (where the truncation matters) come here. */
+__device__ __noinline__ int fb_rice_k_scan(uint64_t sum, int n)
+{
+    int best = 0;
+    uint32_t best_bits = 0xffffffffu;
+#pragma unroll 1
+    for (int k = 0; k <= 30; k++) {
+        uint32_t b = (uint32_t)fb_rice_count64(sum, n, k);
+        if (b < best_bits) { best_bits = b; best = k; }
+    }
+    return best;
+}
+
+/* rice.c:30-45.  The cost is convex in k while nothing wraps, which gives the closed form:
+ * smallest k with ((sum - n/2) >> k) <= 2n; otherwise scan. */
 __device__ __forceinline__ int fb_rice_k(uint64_t sum, int n)
 {
     if (sum < 0x80000000ull) {
@@ -144,13 +156,7 @@ __device__ __forceinline__ int fb_rice_k(uint64_t sum, int n)
         if ((su >> k) > t) k++;
         return k > 30 ? 30 : k;
     }
-    int best = 0;
-    uint32_t best_bits = 0xffffffffu;
-    for (int k = 0; k <= 30; k++) {
-        uint32_t b = (uint32_t)fb_rice_count64(sum, n, k);
-        if (b < best_bits) { best_bits = b; best = k; }
-    }
-    return best;
+    return fb_rice_k_scan(sum, n);
 }
 
 /* rice.c:148-155 */

@@ -8,19 +8,21 @@
  * parameter per partition (rice.c:30-74) and the smallest total over the
  * allowed partition orders with ties going to the HIGHER order (rice.c:128-135).
  *
- * Shape of one candidate evaluation:
- *   tiles     every thread owns 16-sample runs; the run and its history come from the
- *             staged plane with 128-bit shared loads, the residuals stay in registers,
- *             one zig-zag sum per run goes to shared memory;
+ * Candidates are evaluated in GROUPS of up to three whose members do not depend on
+ * each other's result (the order searches of optimize.c:205-261 are replayed on
+ * the stored costs afterwards, so the decisions are the reference's):
+ *   tiles     for each member, every thread owns 16-sample runs; the run and its
+ *             history come from the staged plane with 128-bit shared loads, the
+ *             residuals stay in registers, one zig-zag sum per run goes to shared
+ *             memory (one buffer per member);
  *   barrier
- *   finish    warp 0 alone folds the run sums into the partition pyramid with shuffles
- *             (a lane holds 1..8 partitions of the finest level, then pairs merge),
- *             picks parameter and partition order, posts the total;
+ *   finish    one WARP per member folds the run sums into the partition pyramid with
+ *             shuffles (a lane holds 1..8 partitions of the finest level, then pairs
+ *             merge), picks parameter and partition order, posts the total;
  *   barrier
- * All candidate coefficient rows are staged once per subframe, so nothing else
- * separates two candidates.  The Rice parameters of the best candidate so far are
- * kept beside the search, which makes the last pass (optimize.c:266-275) a pure
- * residual store.
+ * All candidate coefficient rows are staged once per subframe.  The Rice parameters
+ * of the best candidate so far are kept beside the search, which makes the last pass
+ * (optimize.c:266-275) a pure residual store.
  */
 #ifndef FLAKE_B200_K_SEARCH_CUH
 #define FLAKE_B200_K_SEARCH_CUH
@@ -29,19 +31,21 @@
 #include "k_lpc.cuh"
 
 #ifndef FB_SEARCH_THREADS
-#define FB_SEARCH_THREADS 64     /* 16 samples per thread and tile; measured best of 32/64/128/256 on B200 */
+#define FB_SEARCH_THREADS 128    /* 16 samples per thread and tile; measured best of 64/96/128/256 on B200 */
 #endif
+
+#define FB_GROUP 3                  /* candidates evaluated between two decisions */
 
 template <int MAXP>
 struct FbSearchShared {
     unsigned long long sums[256];   /* finest-level partition sums when runs do not tile the partitions */
-    uint8_t  kbuf[512];             /* candidate: parameter of partition j at level L at [(1<<L)-1+j] */
+    uint8_t  kbuf[FB_GROUP][512];   /* group member: parameter of partition j at level L at [(1<<L)-1+j] */
     uint8_t  kbest[256];            /* best candidate so far: parameters at its partition order */
     int32_t  coef[MAXP][MAXP];      /* candidate rows (row = order-1), zero padded */
     int32_t  shift[MAXP];
     uint32_t sumabs[MAXP];          /* sum |coef| per row */
-    uint32_t result;
-    int32_t  porder, method;        /* of the candidate just finished */
+    uint32_t result[FB_GROUP];      /* of the group members just finished */
+    int32_t  porder[FB_GROUP], method[FB_GROUP];
     int32_t  best_porder, best_method;
     uint32_t best_bits;
 };
@@ -73,112 +77,117 @@ __device__ __forceinline__ int32_t fb_lpc_residual(const int32_t *x, int i, int 
 /* finish: partition pyramid, Rice parameters, best partition order     */
 /* ------------------------------------------------------------------ */
 /*
- * Warp 0 only.  Finest-level sums come from `runsum` (one per 16-sample run, `per` runs per
- * partition) or, when runsum == NULL, from S.sums.  The pairwise pyramid of rice.c:96-102 is
- * exact integer addition, so the order of summation is free.  Levels are visited from the
- * finest down and a level replaces the best only when strictly smaller, which is the
- * reference's ascending scan with `<=` (ties to the higher order, rice.c:128-135).
- * Posts S.result (rice.c:157-187 total), S.porder, S.method and the parameters in S.kbuf.
+ * One whole warp, for group member `slot`.  F[] holds the finest-level sums: one per
+ * 16-sample run (`per` runs per partition of level pmax), or the partition sums themselves
+ * (per == 1, S.sums).  The pairwise pyramid of rice.c:96-102 is exact integer addition, so a
+ * partition of level L is simply the sum of its per << (pmax - L) entries of F.  Levels of 32
+ * partitions or more are walked lane-strided; the six coarser levels are costed side by side,
+ * one partition per lane group, merged by shuffles.  Levels are compared from the finest down
+ * and replace the best only when strictly smaller, which is the reference's ascending scan
+ * with `<=` (ties to the higher order, rice.c:128-135).
+ * Posts S.result[slot] (rice.c:157-187 total), S.porder[slot], S.method[slot] and the
+ * parameters of every level in S.kbuf[slot].
  */
 template <int MAXP>
-__device__ __forceinline__ void fb_finish_warp0(FbSearchShared<MAXP> &S, const unsigned long long *runsum,
-                                                int per, int n, int is_lpc, int order, int obits,
-                                                int pmin, int pmax)
+__device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, const unsigned long long *F,
+                                               int per, int n, int is_lpc, int order, int obits,
+                                               int pmin, int pmax)
 {
     const int lane = threadIdx.x & 31;
-    unsigned long long s[8];
-#pragma unroll
-    for (int v = 0; v < 8; v++) s[v] = 0;
-    if (pmax >= 5) {
-        const int V = 1 << (pmax - 5);
-#pragma unroll
-        for (int v = 0; v < 8; v++) {
-            if (v < V) {
-                const int p = lane * V + v;
-                if (runsum) {
-                    unsigned long long a = 0;
-                    for (int q = 0; q < per; q++) a += runsum[p * per + q];
-                    s[v] = a;
-                } else {
-                    s[v] = S.sums[p];
-                }
-            }
-        }
-    } else {
-        const int g = 32 >> pmax, j = lane / g, sub = lane % g;
-        unsigned long long a = 0;
-        if (runsum) {
-            for (int q = sub; q < per; q += g) a += runsum[j * per + q];
-            for (int o = 1; o < g; o <<= 1) a += __shfl_xor_sync(FB_FULL_MASK, a, o);
-        } else {
-            a = S.sums[j];
-        }
-        s[0] = a;
-    }
-
+    uint8_t *kbuf = S.kbuf[slot];
     uint32_t best = 0xffffffffu;
     int bl = pmin, bmethod = 0;
-    for (int L = pmax; L >= pmin; L--) {
+    unsigned long long t5 = 0;
+
+    /* levels with 32 partitions or more */
+#pragma unroll 1
+    for (int L = pmax; L >= 5; L--) {
+        const int span = per << (pmax - L);
         uint32_t bits = 0;
         int flag = 0;
-        if (L >= 5) {
-            const int Vc = 1 << (L - 5);
+#pragma unroll 1
+        for (int j = lane; j < (1 << L); j += 32) {
+            const unsigned long long *src = F + j * span;
+            unsigned long long sum = 0;
+#pragma unroll 4
+            for (int q = 0; q < span; q++) sum += src[q];
+            const int cnt = (n >> L) - (j == 0 ? order : 0);
+            const int k = fb_rice_k(sum, cnt);
+            kbuf[(1 << L) - 1 + j] = (uint8_t)k;
+            bits += (uint32_t)fb_rice_count64(sum, cnt, k);
+            flag |= (k > 14);
+            t5 = sum;                                     /* L == 5: the lane's own partition */
+        }
+        const uint32_t tot = __reduce_add_sync(FB_FULL_MASK, bits);
+        const int r2 = __any_sync(FB_FULL_MASK, flag) ? 1 : 0;
+        const uint32_t b = tot + 4u * (1u << L);
+        if (L >= pmin && b < best) { best = b; bl = L; bmethod = r2; }
+    }
+    if (pmax < 5) {
+        /* the lanes of a group share partition lane / g of level pmax */
+        const int g = 32 >> pmax, j = lane / g, sub = lane % g;
+        unsigned long long a = 0;
+        for (int q = sub; q < per; q += g) a += F[j * per + q];
+        for (int o = 1; o < g; o <<= 1) a += __shfl_xor_sync(FB_FULL_MASK, a, o);
+        t5 = a;
+    }
+
+    /* levels 4..0 (and level pmax < 5): t[L] = sum of the partition this lane belongs to.
+     * With pmax < 5 the lanes start out holding level pmax, so the merges above it are skipped. */
+    if (pmin < 5) {
+        unsigned long long t[5];
+        {
+            const unsigned long long o = __shfl_xor_sync(FB_FULL_MASK, t5, 1);
+            t[4] = t5 + (5 <= pmax ? o : 0ull);
+        }
 #pragma unroll
-            for (int v = 0; v < 8; v++) {
-                if (v < Vc) {
-                    const int j = lane * Vc + v;
-                    const int cnt = (n >> L) - (j == 0 ? order : 0);
-                    const int k = fb_rice_k(s[v], cnt);
-                    S.kbuf[(1 << L) - 1 + j] = (uint8_t)k;
-                    bits += (uint32_t)fb_rice_count64(s[v], cnt, k);
-                    flag |= (k > 14);
-                }
-            }
-        } else {
+        for (int L = 4; L >= 1; L--) {
+            const unsigned long long o = __shfl_xor_sync(FB_FULL_MASK, t[L], 1 << (5 - L));
+            t[L - 1] = t[L] + (L <= pmax ? o : 0ull);
+        }
+        uint32_t bits[5];
+        int ks[5];
+#pragma unroll
+        for (int L = 0; L < 5; L++) {
             const int g = 32 >> L, j = lane / g;
             const int cnt = (n >> L) - (j == 0 ? order : 0);
-            const int k = fb_rice_k(s[0], cnt);
-            if ((lane % g) == 0) {
-                S.kbuf[(1 << L) - 1 + j] = (uint8_t)k;
-                bits = (uint32_t)fb_rice_count64(s[0], cnt, k);
-                flag = (k > 14);
-            }
+            const int k = fb_rice_k(t[L], cnt);
+            const bool mine = (lane % g) == 0 && L <= pmax && L >= pmin;
+            ks[L] = k;
+            bits[L] = mine ? (uint32_t)fb_rice_count64(t[L], cnt, k) : 0u;
         }
-        const uint32_t lvl = __reduce_add_sync(FB_FULL_MASK, bits);
-        const int r2 = __any_sync(FB_FULL_MASK, flag) ? 1 : 0;
-        const uint32_t b = lvl + 4u * (1u << L);
-        if (b < best) { best = b; bl = L; bmethod = r2; }
-        if (L > pmin) {
-            if (L > 5) {
-                const int Vh = 1 << (L - 6);
 #pragma unroll
-                for (int v = 0; v < 4; v++)
-                    if (v < Vh) s[v] = s[2 * v] + s[2 * v + 1];
-            } else {
-                s[0] += __shfl_xor_sync(FB_FULL_MASK, s[0], 1 << (5 - L));
-            }
+        for (int L = 4; L >= 0; L--) {
+            const int g = 32 >> L, j = lane / g;
+            const bool mine = (lane % g) == 0 && L <= pmax && L >= pmin;
+            if (mine) kbuf[(1 << L) - 1 + j] = (uint8_t)ks[L];
+            const uint32_t tot = __reduce_add_sync(FB_FULL_MASK, bits[L]);
+            const int r2 = __any_sync(FB_FULL_MASK, mine && ks[L] > 14) ? 1 : 0;
+            const uint32_t b = tot + 4u * (1u << L);
+            if (L <= pmax && L >= pmin && b < best) { best = b; bl = L; bmethod = r2; }
         }
     }
+
     if (lane == 0) {
         uint32_t total = (uint32_t)(order * obits + 2);
         if (is_lpc) total += 4u + 5u + (uint32_t)order * 15u;
         total += best;
         total += (uint32_t)bmethod + 4u;
-        S.result = total;
-        S.porder = bl;
-        S.method = bmethod;
+        S.result[slot] = total;
+        S.porder[slot] = bl;
+        S.method[slot] = bmethod;
     }
 }
 
-/* the candidate just finished is the best so far: warp 0 keeps its parameters */
+/* group member `slot` is the best candidate so far: warp 0 keeps its parameters */
 template <int MAXP>
-__device__ __forceinline__ void fb_keep_best(FbSearchShared<MAXP> &S, uint32_t bits)
+__device__ __forceinline__ void fb_keep_best(FbSearchShared<MAXP> &S, int slot, uint32_t bits)
 {
     if (threadIdx.x < 32) {
         __syncwarp();
-        const int bl = S.porder, np = 1 << bl;
-        for (int j = threadIdx.x; j < np; j += 32) S.kbest[j] = S.kbuf[np - 1 + j];
-        if (threadIdx.x == 0) { S.best_porder = bl; S.best_method = S.method; S.best_bits = bits; }
+        const int bl = S.porder[slot], np = 1 << bl;
+        for (int j = threadIdx.x; j < np; j += 32) S.kbest[j] = S.kbuf[slot][np - 1 + j];
+        if (threadIdx.x == 0) { S.best_porder = bl; S.best_method = S.method[slot]; S.best_bits = bits; }
         __syncwarp();
     }
 }
@@ -196,14 +205,14 @@ __device__ __forceinline__ void fb_store_best(FbSearchShared<MAXP> &S, FbSub *sb
 /*
  * Generic candidate evaluation: any block size, samples through a generic
  * pointer (global memory for blocks that do not fit shared memory).
- * Every thread of the CTA calls it and gets the total
- * (calc_rice_params_fixed / _lpc return value, rice.c:157-187).
+ * Every thread of the CTA calls it; the total (calc_rice_params_fixed / _lpc
+ * return value, rice.c:157-187) lands in S.result[slot].
  * want_sums: cost the candidate; res_out != NULL: store the residual (warm-up = samples).
  */
 template <int MAXP>
-__device__ __noinline__ uint32_t fb_evaluate(FbSearchShared<MAXP> &S, const int32_t *x, int n, int is_lpc, int order,
-                                             int row, int obits, int pmin_cfg, int pmax_cfg,
-                                             int32_t *res_out, bool want_sums)
+__device__ __noinline__ void fb_evaluate(FbSearchShared<MAXP> &S, int slot, const int32_t *x, int n, int is_lpc,
+                                         int order, int row, int obits, int pmin_cfg, int pmax_cfg,
+                                         int32_t *res_out, bool want_sums)
 {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
     const int pmin = fb_limit_porder(pmin_cfg, n, order);
@@ -212,6 +221,7 @@ __device__ __noinline__ uint32_t fb_evaluate(FbSearchShared<MAXP> &S, const int3
     const int32_t *coef = S.coef[row];
     const int shift = S.shift[row];
     if (want_sums) {
+        __syncthreads();                                  /* the previous member's finish is done with S.sums */
         for (int e = tid; e < nparts; e += T) S.sums[e] = 0;
         __syncthreads();
     }
@@ -241,11 +251,9 @@ __device__ __noinline__ uint32_t fb_evaluate(FbSearchShared<MAXP> &S, const int3
         if ((lane == 31 || pn != p) && u)
             atomicAdd(&S.sums[p], u);
     }
-    if (!want_sums) return 0;
+    if (!want_sums) return;
     __syncthreads();
-    if (tid < 32) fb_finish_warp0<MAXP>(S, nullptr, 0, n, is_lpc, order, obits, pmin, pmax);
-    __syncthreads();
-    return S.result;
+    if (tid < 32) fb_finish_warp<MAXP>(S, slot, S.sums, 1, n, is_lpc, order, obits, pmin, pmax);
 }
 
 /* ------------------------------------------------------------------ */
@@ -259,25 +267,97 @@ __device__ __noinline__ uint32_t fb_evaluate(FbSearchShared<MAXP> &S, const int3
  * whose runs are 16 samples apart hit distinct bank groups */
 __host__ __device__ __forceinline__ int fb_skew(int logical) { return logical + ((logical >> 4) << 2); }
 __host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n + FB_HIST + FB_RUN) + 8 + 1) & ~1; }
-/* staged plane + one 64-bit zig-zag sum per 16-sample run, in 32-bit words */
-__host__ __device__ __forceinline__ int fb_search_smem_words(int n) { return fb_skew_words(n) + 2 * (((n + FB_RUN - 1) / FB_RUN) + 2); }
+/* 64-bit zig-zag sums, one per 16-sample run, per group member: words */
+__host__ __device__ __forceinline__ int fb_runsum_words(int n) { return 2 * (((n + FB_RUN - 1) / FB_RUN) + 2); }
+/* staged plane + the run sums of a whole group, in 32-bit words */
+__host__ __device__ __forceinline__ int fb_search_smem_words(int n) { return fb_skew_words(n) + FB_GROUP * fb_runsum_words(n); }
 /* word offset of logical (16 m + d) relative to that of logical 16 m; d may be negative */
 __host__ __device__ constexpr int fb_skew_delta(int d) { return d + 4 * (d >= 0 ? d / 16 : -((-d + 15) / 16)); }
 
+#define FB_SUMS  1                /* cost the candidate: zig-zag sums */
+#define FB_STORE 2                /* write the residual to global memory */
+
+/* Cold paths of a run, out of line so that the hot body stays small (the kernel is bound by
+ * instruction fetch before anything else). */
+
+/* a run that crosses the end of the block: per sample, 64-bit, straight from the staged plane */
+template <int MAXP>
+__device__ __noinline__ void fb_run_tail(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int order, int row,
+                                         int psize, int i0, int32_t *res_out, unsigned long long *runsum, int mode)
+{
+    const int32_t *coef = S.coef[row];
+    const int shift = S.shift[row];
+    unsigned long long acc = 0;
+    int pcur = -1;
+    for (int i = i0; i < n && i < i0 + FB_RUN; i++) {
+        const int32_t xi = xs[fb_skew(i + FB_HIST)];
+        int32_t r = xi;
+        if (i >= order) {
+            long long pred = 0;
+            for (int j = 0; j < order; j++)
+                pred += (long long)coef[j] * (long long)xs[fb_skew(i - 1 - j + FB_HIST)];
+            r = (int32_t)((long long)xi - (pred >> shift));
+        }
+        if (mode & FB_STORE) res_out[i] = r;
+        if ((mode & FB_SUMS) && i >= order) {
+            if (!runsum) {
+                const int pi = i / psize;
+                if (pi != pcur) {
+                    if (acc) atomicAdd(&S.sums[pcur], acc);
+                    acc = 0; pcur = pi;
+                }
+            }
+            acc += fb_zigzag(r);
+        }
+    }
+    if (mode & FB_SUMS) {
+        if (runsum) runsum[i0 >> 4] = acc;
+        else if (acc) atomicAdd(&S.sums[pcur], acc);
+    }
+}
+
+/* full run whose partitions are not whole runs: walk it, flushing at partition boundaries */
+template <int MAXP>
+__device__ __noinline__ void fb_run_scatter(FbSearchShared<MAXP> &S, int i0, int order, int psize,
+                                            int4 r0, int4 r1, int4 r2, int4 r3)
+{
+    const int32_t r[FB_RUN] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
+                               r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+    unsigned long long acc = 0;
+    int pcur = -1;
+    for (int k = 0; k < FB_RUN; k++) {
+        const int i = i0 + k;
+        if (i < order) continue;
+        const int pi = i / psize;
+        if (pi != pcur) {
+            if (acc) atomicAdd(&S.sums[pcur], acc);
+            acc = 0; pcur = pi;
+        }
+        acc += fb_zigzag(r[k]);
+    }
+    if (acc) atomicAdd(&S.sums[pcur], acc);
+}
+
+/* full run to a destination that is not 16-byte aligned */
+__device__ __noinline__ void fb_run_store_scalar(int32_t *dst, int4 r0, int4 r1, int4 r2, int4 r3)
+{
+    dst[0] = r0.x; dst[1] = r0.y; dst[2] = r0.z; dst[3] = r0.w;
+    dst[4] = r1.x; dst[5] = r1.y; dst[6] = r1.z; dst[7] = r1.w;
+    dst[8] = r2.x; dst[9] = r2.y; dst[10] = r2.z; dst[11] = r2.w;
+    dst[12] = r3.x; dst[13] = r3.y; dst[14] = r3.z; dst[15] = r3.w;
+}
+
 /*
- * Residual of the samples [i0, i0+16) with a register sliding window.
+ * Residual of the full run [i0, i0+16) with a register sliding window.
  * P = predictor order rounded up to a multiple of 4 (coefficients beyond the
  * order are zero).  WIDE: 64-bit prediction and sums (always exact);
  * !WIDE: 32-bit, used only when the caller proved nothing can overflow.
  */
-template <int MAXP, int P, bool WIDE>
-__device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int order,
-                                                int row, int psize, int tile_base,
-                                                int32_t *res_out, unsigned long long *runsum, bool want_sums)
+template <int MAXP, int P, bool WIDE, int MODE>
+__device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const int32_t *xs, int order,
+                                                int row, int psize, int i0,
+                                                int32_t *res_out, unsigned long long *runsum)
 {
-    const int tid = threadIdx.x;
-    const int i0 = tile_base + tid * FB_RUN;
-    if (i0 >= n) return;
     int32_t c[P];
 #pragma unroll
     for (int g = 0; g < P / 4; g++) {
@@ -310,111 +390,82 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const i
             r[k] = w[P + k] - (pred >> shift);
         }
     }
-    if (i0 < order) {                                         /* warm-up samples pass through */
+    /* zig-zag sum of the run (rice.c:76-95) */
+    unsigned long long acc = 0;
+    if (MODE & FB_SUMS) {
+        if (WIDE) {
 #pragma unroll
-        for (int k = 0; k < FB_RUN; k++) if (i0 + k < order) r[k] = w[P + k];
+            for (int k = 0; k < FB_RUN; k++) acc += fb_zigzag(r[k]);
+        } else {
+            uint32_t a32 = 0;
+#pragma unroll
+            for (int k = 0; k < FB_RUN; k++) a32 += fb_zigzag(r[k]);
+            acc = a32;
+        }
     }
-    if (res_out) {
+    if (i0 < order) {                                         /* warm-up samples pass through, uncounted */
+#pragma unroll
+        for (int k = 0; k < FB_RUN; k++) {
+            if (i0 + k < order) {
+                if (MODE & FB_SUMS) acc -= fb_zigzag(r[k]);
+                r[k] = w[P + k];
+            }
+        }
+    }
+    if (MODE & FB_STORE) {
         int32_t *dst = res_out + i0;
-        if (i0 + FB_RUN <= n && (((size_t)dst) & 15u) == 0) {
+        if ((((size_t)dst) & 15u) == 0) {
 #pragma unroll
             for (int g = 0; g < FB_RUN / 4; g++)
                 reinterpret_cast<int4 *>(dst)[g] = make_int4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         } else {
-#pragma unroll
-            for (int k = 0; k < FB_RUN; k++) if (i0 + k < n) dst[k] = r[k];
+            fb_run_store_scalar(dst, make_int4(r[0], r[1], r[2], r[3]), make_int4(r[4], r[5], r[6], r[7]),
+                                make_int4(r[8], r[9], r[10], r[11]), make_int4(r[12], r[13], r[14], r[15]));
         }
     }
-    if (!want_sums) return;
-
-    /* zig-zag sums (rice.c:76-95).  Partitions that are whole multiples of the run length
-     * (the rule for every power-of-two block size): one sum per run, folded into the
-     * partition sums by the finishing warp -- no atomics on the hot loop. */
-    if (runsum) {
-        unsigned long long acc;
-        if (i0 >= order && i0 + FB_RUN <= n) {
-            if (WIDE) {
-                acc = 0;
-#pragma unroll
-                for (int k = 0; k < FB_RUN; k++) acc += fb_zigzag(r[k]);
-            } else {
-                uint32_t a32 = 0;
-#pragma unroll
-                for (int k = 0; k < FB_RUN; k++) a32 += fb_zigzag(r[k]);
-                acc = a32;
-            }
-        } else {
-            acc = 0;
-#pragma unroll
-            for (int k = 0; k < FB_RUN; k++)
-                if (i0 + k >= order && i0 + k < n) acc += fb_zigzag(r[k]);
-        }
-        runsum[i0 >> 4] = acc;
-        return;
-    }
-    /* general partition sizes: walk the run, flushing at partition boundaries */
-    {
-        const int istart = i0 < order ? order : i0;
-        int pcur = istart / psize;
-        int nb = (pcur + 1) * psize;
-        unsigned long long acc = 0;
-#pragma unroll 1
-        for (int k = 0; k < FB_RUN; k++) {
-            const int i = i0 + k;
-            if (i < order || i >= n) continue;
-            if (i >= nb) {
-                if (acc) atomicAdd(&S.sums[pcur], acc);
-                acc = 0; pcur++; nb += psize;
-            }
-            /* r[] lives in registers: select without dynamic indexing */
-            int32_t rv = 0;
-#pragma unroll
-            for (int q = 0; q < FB_RUN; q++) rv = (q == k) ? r[q] : rv;
-            acc += fb_zigzag(rv);
-        }
-        if (acc) atomicAdd(&S.sums[pcur], acc);
+    if (MODE & FB_SUMS) {
+        /* partitions that are whole multiples of the run length (the rule for every
+         * power-of-two block size): one sum per run, folded into the partition sums by the
+         * finishing warp -- no atomics on the hot loop */
+        if (runsum) runsum[i0 >> 4] = acc;
+        else fb_run_scatter<MAXP>(S, i0, order, psize, make_int4(r[0], r[1], r[2], r[3]), make_int4(r[4], r[5], r[6], r[7]),
+                                  make_int4(r[8], r[9], r[10], r[11]), make_int4(r[12], r[13], r[14], r[15]));
     }
 }
 
-template <int MAXP, int P, bool WIDE>
+template <int MAXP, int P, bool WIDE, int MODE>
 __device__ __noinline__ void fb_tiles(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int order, int row, int psize,
-                                      int32_t *res_out, unsigned long long *runsum, bool want_sums)
+                                      int32_t *res_out, unsigned long long *runsum)
 {
-    for (int tile = 0; tile < n; tile += (int)blockDim.x * FB_RUN)
-        fb_run_residual<MAXP, P, WIDE>(S, xs, n, order, row, psize, tile, res_out, runsum, want_sums);
+    for (int i0 = (int)threadIdx.x * FB_RUN; i0 < n; i0 += (int)blockDim.x * FB_RUN) {
+        if (i0 + FB_RUN <= n) fb_run_residual<MAXP, P, WIDE, MODE>(S, xs, order, row, psize, i0, res_out, runsum);
+        else fb_run_tail<MAXP>(S, xs, n, order, row, psize, i0, res_out, runsum, MODE);
+    }
 }
 
 /*
- * Fast evaluation of the candidate in row `row` of S.coef (fixed predictors: binomial
- * coefficients, shift 0).  `maxabs` bounds |sample| and decides whether 32-bit
- * arithmetic is provably exact:
+ * Residual pass of the candidate in row `row` of S.coef over the staged block (fixed
+ * predictors: binomial coefficients, shift 0); no barrier inside.  `maxabs` bounds |sample|
+ * and decides whether 32-bit arithmetic is provably exact:
  *   |pred| <= sum|c| * maxabs < 2^31, and
  *   |residual| <= maxabs + (sum|c|*maxabs >> shift) + 1 < 2^26 so that a run's
  *   zig-zag sum fits 32 bits.
+ * MODE: FB_SUMS, FB_STORE or both.  runsum == NULL with FB_SUMS: partition sums by atomics
+ * into S.sums (zeroed by the caller).
  */
-template <int MAXP>
-__device__ __noinline__ uint32_t fb_evaluate_fast(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int order,
-                                                  int row, int obits, int pmin_cfg, int pmax_cfg, uint32_t maxabs,
-                                                  int32_t *res_out, bool want_sums)
+template <int MAXP, int MODE>
+__device__ __noinline__ void fb_residual_pass(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int order, int row,
+                                              int psize, uint32_t maxabs, int32_t *res_out,
+                                              unsigned long long *runsum)
 {
-    const int pmin = fb_limit_porder(pmin_cfg, n, order);
-    const int pmax = fb_limit_porder(pmax_cfg, n, order);
-    const int nparts = 1 << pmax, psize = n >> pmax;
     const unsigned long long pm = (unsigned long long)S.sumabs[row] * (unsigned long long)maxabs;
     const bool narrow = pm < 0x80000000ull &&
                         ((unsigned long long)maxabs + (pm >> S.shift[row]) + 1ull) < (1ull << 26);
     const int P = (order + 3) & ~3;
-    /* per-run sums are usable when every partition is a whole number of runs */
-    unsigned long long *runsum = (psize % FB_RUN) == 0
-        ? reinterpret_cast<unsigned long long *>(const_cast<int32_t *>(xs) + fb_skew_words(n)) : nullptr;
-    if (want_sums && !runsum) {
-        for (int e = threadIdx.x; e < nparts; e += blockDim.x) S.sums[e] = 0;
-        __syncthreads();
-    }
 #define FB_CASE(PP)                                                                                         \
     case PP:                                                                                                \
-        if (narrow) fb_tiles<MAXP, PP, false>(S, xs, n, order, row, psize, res_out, runsum, want_sums);     \
-        else        fb_tiles<MAXP, PP, true>(S, xs, n, order, row, psize, res_out, runsum, want_sums);      \
+        if (narrow) fb_tiles<MAXP, PP, false, MODE>(S, xs, n, order, row, psize, res_out, runsum);          \
+        else        fb_tiles<MAXP, PP, true, MODE>(S, xs, n, order, row, psize, res_out, runsum);           \
         break;
     switch (P) {
         case 0:
@@ -424,28 +475,89 @@ __device__ __noinline__ uint32_t fb_evaluate_fast(FbSearchShared<MAXP> &S, const
                 switch (P) {
                     FB_CASE(16) FB_CASE(20) FB_CASE(24) FB_CASE(28)
                     default:
-                        if (narrow) fb_tiles<MAXP, 32, false>(S, xs, n, order, row, psize, res_out, runsum, want_sums);
-                        else        fb_tiles<MAXP, 32, true>(S, xs, n, order, row, psize, res_out, runsum, want_sums);
+                        if (narrow) fb_tiles<MAXP, 32, false, MODE>(S, xs, n, order, row, psize, res_out, runsum);
+                        else        fb_tiles<MAXP, 32, true, MODE>(S, xs, n, order, row, psize, res_out, runsum);
                         break;
                 }
             }
             break;
     }
 #undef FB_CASE
-    if (!want_sums) return 0;
-    __syncthreads();
-    if (threadIdx.x < 32) fb_finish_warp0<MAXP>(S, runsum, psize / FB_RUN, n, is_lpc, order, obits, pmin, pmax);
-    __syncthreads();
-    return S.result;
 }
 
-/* one candidate through whichever path the block size allows */
-#define FB_EVAL(is_lpc_, order_, row_, res_, sums_)                                                           \
-    (fast ? fb_evaluate_fast<MAXP>(S, xs, n, (is_lpc_), (order_), (row_), obits, pmin, pmax, maxabs, (res_), (sums_)) \
-          : fb_evaluate<MAXP>(S, xg, n, (is_lpc_), (order_), (row_), obits, pmin, pmax, (res_), (sums_)))
+/* what a group evaluation needs to know about the subframe */
+struct FbSearchCtx {
+    const int32_t *xs;          /* staged plane (fast) */
+    const int32_t *xg;          /* plane in global memory */
+    int n, obits, pmin, pmax, is_lpc;
+    uint32_t maxabs;
+    bool fast, tileable;        /* tileable: every partition size is a whole number of runs */
+};
+
+/*
+ * Cost `count` (<= FB_GROUP) candidates of orders ord[]; totals land in S.result[0..count).
+ * Every thread of the CTA calls it.  res_out != NULL (count == 1 only): the same pass also
+ * stores the residual -- the orders that are not searched (optimize.c:196-204) need one pass.
+ */
+template <int MAXP>
+__device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSearchCtx &X, int count, const int *ord,
+                                           int32_t *res_out)
+{
+    const int tid = threadIdx.x;
+    if (count <= 0) return;
+    if (X.fast && X.tileable) {
+        unsigned long long *runsum0 = reinterpret_cast<unsigned long long *>(const_cast<int32_t *>(X.xs) + fb_skew_words(X.n));
+        const int rstride = fb_runsum_words(X.n) / 2;
+        for (int s = 0; s < count; s++) {
+            const int order = ord[s], row = X.is_lpc ? order - 1 : order;
+            const int pmax = fb_limit_porder(X.pmax, X.n, order);
+            if (res_out) fb_residual_pass<MAXP, FB_SUMS | FB_STORE>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, res_out, runsum0);
+            else fb_residual_pass<MAXP, FB_SUMS>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, nullptr, runsum0 + s * rstride);
+        }
+        __syncthreads();
+        for (int s = tid >> 5; s < count; s += (int)(blockDim.x >> 5)) {
+            const int order = ord[s];
+            const int pmin = fb_limit_porder(X.pmin, X.n, order);
+            const int pmax = fb_limit_porder(X.pmax, X.n, order);
+            fb_finish_warp<MAXP>(S, s, runsum0 + s * rstride, (X.n >> pmax) / FB_RUN, X.n, X.is_lpc, order, X.obits, pmin, pmax);
+        }
+        __syncthreads();
+        return;
+    }
+    for (int s = 0; s < count; s++) {
+        const int order = ord[s], row = X.is_lpc ? order - 1 : order;
+        if (X.fast) {
+            const int pmin = fb_limit_porder(X.pmin, X.n, order);
+            const int pmax = fb_limit_porder(X.pmax, X.n, order);
+            __syncthreads();
+            for (int e = tid; e < (1 << pmax); e += (int)blockDim.x) S.sums[e] = 0;
+            __syncthreads();
+            if (res_out) fb_residual_pass<MAXP, FB_SUMS | FB_STORE>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, res_out, nullptr);
+            else fb_residual_pass<MAXP, FB_SUMS>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, nullptr, nullptr);
+            __syncthreads();
+            if (tid < 32) fb_finish_warp<MAXP>(S, s, S.sums, 1, X.n, X.is_lpc, order, X.obits, pmin, pmax);
+        } else {
+            fb_evaluate<MAXP>(S, s, X.xg, X.n, X.is_lpc, order, row, X.obits, X.pmin, X.pmax, res_out, true);
+        }
+    }
+    __syncthreads();
+}
+
+/* residual of the chosen predictor to global memory (optimize.c:266-275), no costing */
+template <int MAXP>
+__device__ __forceinline__ void fb_store_residual(FbSearchShared<MAXP> &S, const FbSearchCtx &X, int order, int32_t *rg)
+{
+    const int row = X.is_lpc ? order - 1 : order;
+    if (X.fast) fb_residual_pass<MAXP, FB_STORE>(S, X.xs, X.n, order, row, X.n, X.maxabs, rg, nullptr);
+    else        fb_evaluate<MAXP>(S, 0, X.xg, X.n, X.is_lpc, order, row, X.obits, X.pmin, X.pmax, rg, false);
+}
+
+#ifndef FB_SEARCH_MINBLOCKS
+#define FB_SEARCH_MINBLOCKS 1
+#endif
 
 template <int MAXP>
-__global__ void __launch_bounds__(FB_SEARCH_THREADS)
+__global__ void __launch_bounds__(FB_SEARCH_THREADS, FB_SEARCH_MINBLOCKS)
 k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
          int32_t *res, FbSub *subs, const int32_t *coefs, const int32_t *shifts, int smem_ints)
 {
@@ -465,7 +577,6 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     const int32_t *xg = smp + off;
     int32_t *rg = res + off;
     const int obits = sb->obits;
-    const uint32_t maxabs = sb->maxabs;
 
     /* CONSTANT, optimize.c:143-151 */
     if (sb->is_const) {
@@ -491,9 +602,18 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         for (int i = n + tid; i < n + FB_RUN; i += T) xs[fb_skew(i + FB_HIST)] = 0;
     }
 
-    const int pmin = cfg.min_porder, pmax = cfg.max_porder;
     int min_order = cfg.min_order, max_order = cfg.max_order;
     const bool fixed = (cfg.prediction_type == 1 || n <= max_order);
+
+    FbSearchCtx X;
+    X.xs = xs; X.xg = xg; X.n = n; X.obits = obits;
+    X.pmin = cfg.min_porder; X.pmax = cfg.max_porder; X.is_lpc = fixed ? 0 : 1;
+    X.maxabs = sb->maxabs; X.fast = fast;
+    {
+        /* the finest partition any candidate can use: larger ones are multiples of it */
+        const int pfin = fb_limit_porder(cfg.max_porder, n, 0);
+        X.tileable = ((n >> pfin) % FB_RUN) == 0;
+    }
 
     /* candidate rows: binomial coefficients (optimize.c:44-66 is LPC with shift 0) or the
      * quantised rows of k_lpc; sum |c| per row for the 32-bit exactness test */
@@ -527,72 +647,115 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     if (fast) fb_cp_async_wait_all();
     __syncthreads();
 
+    int ord[FB_GROUP];
+
     /* FIXED, optimize.c:168-190: row = order (row 0 is the all-zero order-0 predictor) */
     if (fixed) {
         if (max_order > 4) max_order = 4;
         int opt = min_order;
         uint32_t best = 0xffffffffu;
-        for (int i = min_order; i <= max_order; i++) {
-            const uint32_t b = FB_EVAL(0, i, i, nullptr, true);
-            if (b < best) { best = b; opt = i; fb_keep_best<MAXP>(S, b); }
+        for (int base = min_order; base <= max_order; base += FB_GROUP) {
+            int cnt = 0;
+            for (int i = base; i <= max_order && cnt < FB_GROUP; i++) ord[cnt++] = i;
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            for (int s = 0; s < cnt; s++) {
+                const uint32_t b = S.result[s];
+                if (b < best) { best = b; opt = ord[s]; fb_keep_best<MAXP>(S, s, b); }
+            }
         }
-        if (opt > 4 || best == 0xffffffffu) {   /* min_order > 4 with a tiny last block: undefined in the reference */
-            if (opt > 4) opt = 4;
-            const uint32_t b = FB_EVAL(0, opt, opt, nullptr, true);
-            fb_keep_best<MAXP>(S, b);
+        if (best == 0xffffffffu) {      /* min_order > 4 with a tiny last block: undefined in the reference */
+            opt = opt > 4 ? 4 : opt;
+            ord[0] = opt;
+            fb_eval_group<MAXP>(S, X, 1, ord, rg);
+            fb_keep_best<MAXP>(S, 0, S.result[0]);
+        } else {
+            fb_store_residual<MAXP>(S, X, opt, rg);
         }
         if (tid == 0) { sb->type = 8; sb->order = opt; }
-        FB_EVAL(0, opt, opt, rg, false);
         fb_store_best<MAXP>(S, sb);
         return;
     }
 
-    /* LPC, optimize.c:193-275 */
+    /* LPC, optimize.c:193-275.  Orders are 0-based indices (order - 1) while searching. */
     const int om = cfg.order_method;
-    int opt_order;                       /* 0-based index while searching */
-    bool have_best = false;
-
-#define FB_EVAL_INDEX(idx, out_bits) (out_bits) = FB_EVAL(1, (idx) + 1, (idx), nullptr, true)
+    int opt_order;
+    uint32_t best = 0xffffffffu;
 
     if (om == 0) {
         opt_order = max_order - 1;
     } else if (om == 1) {
         opt_order = sb->est_order - 1;
     } else if (om >= 2 && om <= 4) {
+        /* optimize.c:205-222: `levels` fixed orders, highest first */
         const int levels = 1 << (om - 1);
-        uint32_t best = 0xffffffffu;
         opt_order = max_order - 1;
-        for (int i = levels - 1; i >= 0; i--) {
-            int order = min_order + (((max_order - min_order + 1) * (i + 1)) / levels) - 2;
-            if (order < 0) order = 0;
-            uint32_t b;
-            FB_EVAL_INDEX(order, b);
-            if (b < best) { best = b; opt_order = order; have_best = true; fb_keep_best<MAXP>(S, b); }
+        for (int base = levels - 1; base >= 0; base -= FB_GROUP) {
+            int cnt = 0, idx[FB_GROUP];
+            for (int i = base; i >= 0 && cnt < FB_GROUP; i--) {
+                int order = min_order + (((max_order - min_order + 1) * (i + 1)) / levels) - 2;
+                if (order < 0) order = 0;
+                idx[cnt] = order; ord[cnt] = order + 1; cnt++;
+            }
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            for (int s = 0; s < cnt; s++) {
+                const uint32_t b = S.result[s];
+                if (b < best) { best = b; opt_order = idx[s]; fb_keep_best<MAXP>(S, s, b); }
+            }
         }
     } else if (om == 5) {
-        uint32_t best = 0xffffffffu;
+        /* optimize.c:223-240: every order */
         opt_order = 0;
-        for (int i = 0; i < max_order; i++) {
-            uint32_t b;
-            FB_EVAL_INDEX(i, b);
-            if (b < best) { best = b; opt_order = i; have_best = true; fb_keep_best<MAXP>(S, b); }
+        for (int base = 0; base < max_order; base += FB_GROUP) {
+            int cnt = 0;
+            for (int i = base; i < max_order && cnt < FB_GROUP; i++) ord[cnt++] = i + 1;
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            for (int s = 0; s < cnt; s++) {
+                const uint32_t b = S.result[s];
+                if (b < best) { best = b; opt_order = base + s; fb_keep_best<MAXP>(S, s, b); }
+            }
         }
     } else {
-        /* log search, optimize.c:241-261 */
-        uint32_t best = 0xffffffffu, done = 0;
-        opt_order = min_order - 1 + (max_order - min_order) / 3;
-        for (int step = 16; step > 0; step >>= 1) {
-            const int last = opt_order;
-            for (int i = last - step; i <= last + step; i += step) {
-                if (i < min_order - 1 || i >= max_order || ((done >> i) & 1u)) continue;
-                uint32_t b;
-                FB_EVAL_INDEX(i, b);
-                done |= 1u << i;
-                if (b < best) { best = b; opt_order = i; have_best = true; fb_keep_best<MAXP>(S, b); }
+        /* log search, optimize.c:241-261.  A step's candidates are last-step, last, last+step.
+         * Steps are merged into one group while the candidate set of the next step does not
+         * depend on the pending results (it is the same for every order that could be `last`
+         * by then); the steps are then replayed on the stored totals. */
+        uint32_t done = 0;
+        const int lo = min_order - 1, hi = max_order - 1;
+        opt_order = lo + (max_order - min_order) / 3;
+        int step = 16;
+        while (step > 0) {
+            int cnt = 0, idx[FB_GROUP], nsteps = 0;
+            uint32_t gmask = 0, hyp = 1u << opt_order;
+            for (int s = step; s > 0; s >>= 1) {
+                uint32_t cfirst = 0;
+                bool same = true, first = true;
+                for (uint32_t hm = hyp; hm; hm &= hm - 1) {
+                    const int h = __ffs((int)hm) - 1;
+                    uint32_t cm = 0;
+                    for (int i = h - s; i <= h + s; i += s)
+                        if (i >= lo && i <= hi) cm |= 1u << i;
+                    cm &= ~(done | gmask);
+                    if (first) { cfirst = cm; first = false; }
+                    else if (cm != cfirst) same = false;
+                }
+                if (!same || cnt + __popc(cfirst) > FB_GROUP) break;
+                for (uint32_t m = cfirst; m; m &= m - 1) { idx[cnt] = __ffs((int)m) - 1; ord[cnt] = idx[cnt] + 1; cnt++; }
+                gmask |= cfirst; hyp |= cfirst; nsteps++;
+            }
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            for (int k = 0; k < nsteps; k++, step >>= 1) {
+                const int last = opt_order;
+                for (int i = last - step; i <= last + step; i += step) {
+                    if (i < lo || i > hi || ((done >> i) & 1u)) continue;
+                    int s = 0;
+                    for (int q = 1; q < FB_GROUP; q++) if (q < cnt && idx[q] == i) s = q;
+                    const uint32_t b = S.result[s];
+                    done |= 1u << i;
+                    if (b < best) { best = b; opt_order = i; fb_keep_best<MAXP>(S, s, b); }
+                }
             }
         }
     }
-#undef FB_EVAL_INDEX
 
     /* final pass for the chosen order, optimize.c:266-275: the costing of a searched order is
      * already known, only its residual is missing */
@@ -600,15 +763,15 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         const int idx = opt_order;
         if (tid < FB_MAX_ORDER) sb->coefs[tid] = (tid <= idx && tid < MAXP) ? S.coef[idx][tid] : 0;
         if (tid == 0) { sb->type = 32; sb->order = idx + 1; sb->shift = S.shift[idx]; }
-        if (have_best) {
-            FB_EVAL(1, idx + 1, idx, rg, false);
+        if (best == 0xffffffffu) {                       /* no search ran (or nothing beat 2^32-1) */
+            ord[0] = idx + 1;
+            fb_eval_group<MAXP>(S, X, 1, ord, rg);
+            fb_keep_best<MAXP>(S, 0, S.result[0]);
         } else {
-            const uint32_t b = FB_EVAL(1, idx + 1, idx, rg, true);
-            fb_keep_best<MAXP>(S, b);
+            fb_store_residual<MAXP>(S, X, idx + 1, rg);
         }
         fb_store_best<MAXP>(S, sb);
     }
 }
-#undef FB_EVAL
 
 #endif

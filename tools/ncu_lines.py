@@ -77,3 +77,35 @@ if os.environ.get("FB_SASS"):
         off = int(r[ia], 16) - base
         loc, txt = sec.get(off, (None, "?"))
         print("%6x %9s  %-50s | %-40s %s" % (off, r[ie], r[isrc].strip()[:50], txt[:40], loc[0] if loc else None))
+if os.environ.get("FB_FUNCS"):
+    # per device function (noinline callee labels inside the kernel's section): instructions, samples, no_inst stalls
+    fn_at, curfn = {}, short
+    sec_name = cands[0]
+    for ln in dis.splitlines():
+        pass
+    insec = False
+    for ln in dis.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+        if m:
+            insec = (m.group(1) == sec_name); curfn = short; continue
+        if not insec:
+            continue
+        m = re.match(r"\s*\.type\s+\$[^$]+\$(\S+),@function", ln)
+        if m:
+            curfn = m.group(1); continue
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
+        if m:
+            fn_at[int(m.group(1), 16)] = curfn
+    cols = {c: hdr.index(c) for c in ("stall_no_inst", "stall_barrier", "stall_wait", "stall_long_sb", "stall_short_sb", "stall_math", "stall_selected", "stall_branch_resolving")}
+    agg = collections.defaultdict(lambda: collections.Counter())
+    for r in data:
+        off = int(r[ia], 16) - base
+        fn = fn_at.get(off, "?")
+        a = agg[fn]
+        a["inst"] += int(r[ie] or 0); a["samples"] += int(r[isamp] or 0); a["size"] += 1
+        for c, i in cols.items():
+            a[c] += int(r[i] or 0)
+    print("---- per function: size inst%% samples%% | " + " ".join(c.replace("stall_", "") for c in cols))
+    for fn, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"]):
+        print("%5d %5.1f%% %5.1f%% | %s  %s" % (a["size"], 100.0 * a["inst"] / max(1, tot), 100.0 * a["samples"] / max(1, tots),
+              " ".join("%6d" % a[c] for c in cols), fn[:70]))

@@ -43,6 +43,7 @@ struct FbEngine {
     uint64_t *d_frame_off;
     uint32_t *d_vbs_sizes, *d_vbs_counts;
     uint16_t *d_xpow32;             /* x^(32 j) mod P, CRC-16 chunk merge (k_pack) */
+    uint32_t *d_crc16tab;           /* CRC-16 slicing tables [4][256] uint16 (k_pack) */
     int search_smem_ints, pack_smem_words;
     uint64_t launches;
     /* optional per-kernel CUDA-event timing (bench.py roofline) */
@@ -133,7 +134,7 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     {
         /* x^(32 j) mod (x^16 + x^15 + x^2 + 1): j zero words appended to a CRC (crc.c:24-46) */
         const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
-        const size_t nent = (size_t)((capb + 3u) >> 2) + 64;
+        const size_t nent = (size_t)((capb + 3u) >> 2) + 1024 + 64;   /* per * (threads - 1) < words + threads */
         uint16_t *tab = (uint16_t *)malloc(nent * sizeof(uint16_t));
         if (!tab) { set_err(err, errlen, "out of host memory", cudaSuccess); fb_engine_destroy(e); return nullptr; }
         uint32_t r = 1;
@@ -144,6 +145,22 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
         cudaError_t ce_ = cudaMalloc((void **)&e->d_xpow32, nent * sizeof(uint16_t));
         if (ce_ == cudaSuccess) ce_ = cudaMemcpy(e->d_xpow32, tab, nent * sizeof(uint16_t), cudaMemcpyHostToDevice);
         free(tab);
+        if (ce_ != cudaSuccess) { set_err(err, errlen, "CRC table upload failed", ce_); fb_engine_destroy(e); return nullptr; }
+    }
+    {
+        /* slicing tables of crc.c's CRC-16 (poly 0x8005, init 0, MSB first):
+         * tab[t][b] = CRC of byte b followed by t zero bytes */
+        uint16_t tab[4][256];
+        for (int b = 0; b < 256; b++) {
+            uint32_t c = 0;
+            for (int t = 0; t < 4; t++) {
+                c ^= (t == 0 ? (uint32_t)b : 0u) << 8;
+                for (int i = 0; i < 8; i++) c = (c & 0x8000u) ? ((c << 1) ^ 0x8005u) & 0xffffu : (c << 1) & 0xffffu;
+                tab[t][b] = (uint16_t)c;
+            }
+        }
+        cudaError_t ce_ = cudaMalloc((void **)&e->d_crc16tab, sizeof tab);
+        if (ce_ == cudaSuccess) ce_ = cudaMemcpy(e->d_crc16tab, tab, sizeof tab, cudaMemcpyHostToDevice);
         if (ce_ != cudaSuccess) { set_err(err, errlen, "CRC table upload failed", ce_); fb_engine_destroy(e); return nullptr; }
     }
     cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
@@ -161,7 +178,7 @@ extern "C" void fb_engine_destroy(FbEngine *e)
     cudaFree(e->d_frames); cudaFree(e->d_nframes); cudaFree(e->d_subs); cudaFree(e->d_modes);
     cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
     cudaFree(e->d_win); cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
-    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32);
+    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32); cudaFree(e->d_crc16tab);
     if (e->tev[0][0])
         for (int p = 0; p < FB_TIMING_RING; p++)
             for (int i = 0; i <= FB_NUM_STAGES; i++) cudaEventDestroy(e->tev[p][i]);
@@ -247,7 +264,7 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     FB_MARK(4);
     FB_LAUNCH(k_pack, dim3(grid_frames), dim3(FB_PACK_THREADS), (size_t)e->pack_smem_words * 4, st,
               cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
-              flen, d_frame_bs, e->d_verbatim, e->pack_smem_words, e->d_xpow32);
+              flen, d_frame_bs, e->d_verbatim, e->pack_smem_words, e->d_xpow32, e->d_crc16tab);
     FB_MARK(5);
     FB_LAUNCH(k_offsets, dim3(1), dim3(1024), 0, st,
               e->d_nframes, flen, e->d_frame_off, d_summary, e->d_verbatim);

@@ -9,8 +9,8 @@
  * run is then emitted MSB-first into a zeroed staging buffer (whole words with
  * plain stores, the two boundary words with atomicOr).  CRC-16 is computed in
  * parallel over 32-bit words with slicing tables and the chunk CRCs are
- * combined with x^(8*len) mod P multipliers (crc.c:24-92 defines P, init 0,
- * no reflection).  The size check that forces VERBATIM subframes
+ * combined with x^(8*len) mod P multipliers, one per chunk (crc.c:24-92 defines
+ * P, init 0, no reflection).  The size check that forces VERBATIM subframes
  * (encode.c:949-964) is evaluated on the exact byte count.
  */
 #ifndef FLAKE_B200_K_PACK_CUH
@@ -157,17 +157,18 @@ __device__ __forceinline__ FbSubLayout fb_sub_layout(const FbSub *sb, int n, boo
 /*
  * frames[f] -> staged bytes at slots + frames[f].slot, frame_len[f].
  * smem_words: capacity of the dynamic shared staging buffer (0: write the
- * global slot directly).  xpow32[j] = x^(32 j) mod P for the CRC-16 merge.
+ * global slot directly).  xpow32[j] = x^(32 j) mod P for the CRC-16 merge;
+ * crc16_tables = the four 256-entry slicing tables (uint16, packed in words).
  */
 __global__ void __launch_bounds__(FB_PACK_THREADS)
 k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
        const int32_t *res, FbSub *subs, const uint8_t *ch_modes, uint8_t *slots,
        uint32_t *frame_len, uint32_t *frame_bs, uint32_t *verbatim_count, int smem_words,
-       const uint16_t *xpow32)
+       const uint16_t *xpow32, const uint32_t *crc16_tables)
 {
     FB_DYN_SMEM(dyn);
     __shared__ uint32_t scan_scratch[33];
-    __shared__ uint16_t crc_tab[4][256];
+    __shared__ __align__(16) uint16_t crc_tab[4][256];
     __shared__ uint32_t s_hdr_len;
     __shared__ uint8_t s_hdr[24];
     __shared__ uint8_t s_params[256];
@@ -185,14 +186,10 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     const bool in_smem = capw <= (uint32_t)smem_words;
     uint32_t *wbuf = in_smem ? (uint32_t *)dyn : gslot;
 
-    /* slicing tables: tab[t][b] = CRC-16 of byte b followed by t zero bytes */
-    for (int b = tid; b < 256; b += T) {
-        uint32_t c = fb_crc16_byte(0, (uint32_t)b);
-        crc_tab[0][b] = (uint16_t)c;
-        c = fb_crc16_byte(c, 0); crc_tab[1][b] = (uint16_t)c;
-        c = fb_crc16_byte(c, 0); crc_tab[2][b] = (uint16_t)c;
-        c = fb_crc16_byte(c, 0); crc_tab[3][b] = (uint16_t)c;
-    }
+    /* slicing tables: tab[t][b] = CRC-16 of byte b followed by t zero bytes (engine.cu) */
+    for (int w = tid; w < 512; w += T) reinterpret_cast<uint32_t *>(&crc_tab[0][0])[w] = crc16_tables[w];
+    /* zero the staging buffer while thread 0 builds the header */
+    for (uint32_t w = tid; w < capw; w += T) wbuf[w] = 0;
 
     /* ---- frame header, encode.c:718-764 (thread 0, byte granular) -------- */
     if (tid == 0) {
@@ -238,9 +235,10 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     uint64_t total_bits = 0;
     bool verbatim = false;
     for (int pass = 0; pass < 2; pass++) {
-        /* zero the staging buffer */
-        for (uint32_t w = tid; w < capw; w += T) wbuf[w] = 0;
-        __syncthreads();
+        if (pass) {                                  /* second try: start from a clean buffer */
+            for (uint32_t w = tid; w < capw; w += T) wbuf[w] = 0;
+            __syncthreads();
+        }
         uint64_t bitpos = (uint64_t)hdr_len * 8u;
         if (tid == 0) {
             FbBitPut b; fb_bp_init(b, wbuf, capw, 0);
@@ -258,19 +256,34 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
             if (rice) for (int j = tid; j < (1 << L.porder); j += T) s_params[j] = sb->params[j];
             __syncthreads();
 
-            /* size my run (partition index tracked incrementally), then scan */
+            /* size my run, then scan.  The partition index is tracked incrementally; 16 samples
+             * that lie in one partition and start 16-byte aligned are taken with four 128-bit
+             * loads and one Rice parameter */
             const int jbeg = rice ? max(i0, L.order) : i0;
             uint32_t mybits = 0;
             if (L.type == 1) {
                 mybits = (uint32_t)(i1 - i0) * (uint32_t)L.obits;
             } else if (rice && jbeg < i1) {
-                int p = jbeg / L.psize;
+                int i = jbeg;
+                int p = i / L.psize;
                 int nb = (p + 1) * L.psize;
                 uint32_t k = s_params[p];
-                if (p > 0 && jbeg == p * L.psize) mybits += (uint32_t)L.pbits;
-                for (int i = jbeg; i < i1; i++) {
+                if (p > 0 && i == p * L.psize) mybits += (uint32_t)L.pbits;
+                while (i < i1) {
                     if (i == nb) { p++; nb += L.psize; k = s_params[p]; mybits += (uint32_t)L.pbits; }
-                    mybits += (fb_zigzag(data[i]) >> k) + 1u + k;
+                    if (i + 16 <= min(i1, nb) && (((size_t)(data + i)) & 15u) == 0) {
+                        const int4 *src = reinterpret_cast<const int4 *>(data + i);
+                        const int4 a = src[0], b = src[1], c4 = src[2], d = src[3];
+                        uint32_t q = (fb_zigzag(a.x) >> k) + (fb_zigzag(a.y) >> k) + (fb_zigzag(a.z) >> k) + (fb_zigzag(a.w) >> k);
+                        q += (fb_zigzag(b.x) >> k) + (fb_zigzag(b.y) >> k) + (fb_zigzag(b.z) >> k) + (fb_zigzag(b.w) >> k);
+                        q += (fb_zigzag(c4.x) >> k) + (fb_zigzag(c4.y) >> k) + (fb_zigzag(c4.z) >> k) + (fb_zigzag(c4.w) >> k);
+                        q += (fb_zigzag(d.x) >> k) + (fb_zigzag(d.y) >> k) + (fb_zigzag(d.z) >> k) + (fb_zigzag(d.w) >> k);
+                        mybits += q + 16u * (k + 1u);
+                        i += 16;
+                    } else {
+                        mybits += (fb_zigzag(data[i]) >> k) + 1u + k;
+                        i++;
+                    }
                 }
             }
             uint32_t sub_tokens;
@@ -323,13 +336,29 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
                 if (L.type == 1) {
                     for (int i = i0; i < i1; i++) fb_bp_put_signed(b, L.obits, data[i]);
                 } else {
-                    int p = jbeg / L.psize;
+                    int i = jbeg;
+                    int p = i / L.psize;
                     int nb = (p + 1) * L.psize;
                     uint32_t k = s_params[p];
-                    if (p > 0 && jbeg == p * L.psize) fb_bp_put(b, (uint32_t)L.pbits, k);
-                    for (int i = jbeg; i < i1; i++) {
+                    if (p > 0 && i == p * L.psize) fb_bp_put(b, (uint32_t)L.pbits, k);
+                    while (i < i1) {
                         if (i == nb) { p++; nb += L.psize; k = s_params[p]; fb_bp_put(b, (uint32_t)L.pbits, k); }
-                        fb_bp_put_rice(b, fb_zigzag(data[i]), k);
+                        if (i + 16 <= min(i1, nb) && (((size_t)(data + i)) & 15u) == 0) {
+                            const int4 *src = reinterpret_cast<const int4 *>(data + i);
+                            const int4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+                            fb_bp_put_rice(b, fb_zigzag(v0.x), k); fb_bp_put_rice(b, fb_zigzag(v0.y), k);
+                            fb_bp_put_rice(b, fb_zigzag(v0.z), k); fb_bp_put_rice(b, fb_zigzag(v0.w), k);
+                            fb_bp_put_rice(b, fb_zigzag(v1.x), k); fb_bp_put_rice(b, fb_zigzag(v1.y), k);
+                            fb_bp_put_rice(b, fb_zigzag(v1.z), k); fb_bp_put_rice(b, fb_zigzag(v1.w), k);
+                            fb_bp_put_rice(b, fb_zigzag(v2.x), k); fb_bp_put_rice(b, fb_zigzag(v2.y), k);
+                            fb_bp_put_rice(b, fb_zigzag(v2.z), k); fb_bp_put_rice(b, fb_zigzag(v2.w), k);
+                            fb_bp_put_rice(b, fb_zigzag(v3.x), k); fb_bp_put_rice(b, fb_zigzag(v3.y), k);
+                            fb_bp_put_rice(b, fb_zigzag(v3.z), k); fb_bp_put_rice(b, fb_zigzag(v3.w), k);
+                            i += 16;
+                        } else {
+                            fb_bp_put_rice(b, fb_zigzag(data[i]), k);
+                            i++;
+                        }
                     }
                 }
                 fb_bp_finish(b);
@@ -355,9 +384,9 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     /* ---- CRC-16 over the body (crc.c:59-92) ---------------------------------------------
      * The body is cut into T right-aligned chunks of `per` words (virtual zero words in
      * front leave a zero-initialised CRC unchanged, and so do the zero bytes that pad the
-     * first real word); each thread runs slicing-by-4 over its chunk and the chunk CRCs are
-     * merged pairwise: crc(A || B) = crc(A) * x^(8 |B|) + crc(B) over GF(2)[x]/P, with the
-     * multipliers x^(32 * per * 2^level) read from the engine's table. */
+     * first real word); each thread runs slicing-by-4 over its chunk and weighs the chunk CRC
+     * with x^(32 * per * chunks behind it) mod P, read from the engine's table:
+     * crc(A || B) = crc(A) * x^(8 |B|) + crc(B) over GF(2)[x]/P. */
     {
         const uint32_t nwords = (body + 3u) >> 2;
         const uint32_t padbytes = nwords * 4u - body;
@@ -380,19 +409,15 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
             crc = (uint32_t)crc_tab[3][x >> 24] ^ (uint32_t)crc_tab[2][(x >> 16) & 255u] ^
                   (uint32_t)crc_tab[1][(x >> 8) & 255u] ^ (uint32_t)crc_tab[0][x & 255u];
         }
+        /* crc(message) = XOR over chunks of crc(chunk) * x^(8 * bytes behind the chunk) */
+        crc = fb_gf16_mul(crc, xpow32[per * (uint32_t)(T - 1 - tid)]);
         const int lane = tid & 31, warp = tid >> 5;
-        for (int l = 0; l < 5; l++) {
-            const uint32_t m = xpow32[per << l];
-            const uint32_t right = __shfl_down_sync(FB_FULL_MASK, crc, 1u << l);
-            if ((lane & ((2 << l) - 1)) == 0) crc = fb_gf16_mul(crc, m) ^ right;
-        }
+        for (int o = 16; o > 0; o >>= 1) crc ^= __shfl_xor_sync(FB_FULL_MASK, crc, o);
         if (lane == 0) scan_scratch[warp] = crc;
         __syncthreads();
         if (tid == 0) {
-            /* warps in order: acc = acc * x^(8 * bytes per warp) + next */
-            const uint32_t m = xpow32[per << 5];
             uint32_t acc = 0;
-            for (int w = 0; w < (T >> 5); w++) acc = fb_gf16_mul(acc, m) ^ scan_scratch[w];
+            for (int w = 0; w < (T >> 5); w++) acc ^= scan_scratch[w];
             FbBitPut b; fb_bp_init(b, wbuf, capw, (uint64_t)body * 8u);
             fb_bp_put(b, 16, acc);
             fb_bp_finish(b);

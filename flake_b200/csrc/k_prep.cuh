@@ -188,12 +188,68 @@ __device__ __forceinline__ void fb_load_stereo_run(const void *pcm, int fmt, siz
     }
 }
 
+/* decorrelated pair (a, b) of a stereo sample, encode.c:648-694; MODE is the frame's ch_mode */
+template <int MODE>
+__device__ __forceinline__ void fb_decorrelate(int32_t l, int32_t r, int32_t &a, int32_t &b)
+{
+    if (MODE == 10)     { a = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; b = (int32_t)((uint32_t)l - (uint32_t)r); }
+    else if (MODE == 8) { a = l; b = (int32_t)((uint32_t)l - (uint32_t)r); }
+    else if (MODE == 9) { a = (int32_t)((uint32_t)l - (uint32_t)r); b = r; }
+    else                { a = l; b = r; }
+}
+
+/* plane statistics of one channel: OR of all samples (wasted bits), minimum and maximum
+ * (|sample| bound for k_search's 32-bit test; min == max is the CONSTANT test) */
+struct FbPlaneStat { uint32_t orv; int32_t mn, mx; };
+
+/* deinterleave + decorrelate a stereo frame in 8-sample runs, gather the statistics */
+template <int MODE>
+__device__ __forceinline__ void fb_prep_stereo(const void *pcm, int fmt, size_t ibase, int n, int32_t *plane,
+                                               FbPlaneStat &sa, FbPlaneStat &sb)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const bool planes_aligned = ((((size_t)plane) | ((size_t)n * 4u)) & 15u) == 0;
+    for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
+        int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2], av[FB_PREP_RUN], bv[FB_PREP_RUN];
+        fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
+#pragma unroll
+        for (int k = 0; k < FB_PREP_RUN; k++) fb_decorrelate<MODE>(lw[k + 2], rw[k + 2], av[k], bv[k]);
+        if (i + FB_PREP_RUN <= n) {
+#pragma unroll
+            for (int k = 0; k < FB_PREP_RUN; k++) {
+                sa.orv |= (uint32_t)av[k]; sa.mn = min(sa.mn, av[k]); sa.mx = max(sa.mx, av[k]);
+                sb.orv |= (uint32_t)bv[k]; sb.mn = min(sb.mn, bv[k]); sb.mx = max(sb.mx, bv[k]);
+            }
+            if (planes_aligned) {
+                int4 *pa = reinterpret_cast<int4 *>(plane + i), *pb = reinterpret_cast<int4 *>(plane + n + i);
+                pa[0] = make_int4(av[0], av[1], av[2], av[3]); pa[1] = make_int4(av[4], av[5], av[6], av[7]);
+                pb[0] = make_int4(bv[0], bv[1], bv[2], bv[3]); pb[1] = make_int4(bv[4], bv[5], bv[6], bv[7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < FB_PREP_RUN; k++) { plane[i + k] = av[k]; plane[n + i + k] = bv[k]; }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < FB_PREP_RUN; k++) {
+                if (i + k < n) {
+                    sa.orv |= (uint32_t)av[k]; sa.mn = min(sa.mn, av[k]); sa.mx = max(sa.mx, av[k]);
+                    sb.orv |= (uint32_t)bv[k]; sb.mn = min(sb.mn, bv[k]); sb.mx = max(sb.mx, bv[k]);
+                    plane[i + k] = av[k]; plane[n + i + k] = bv[k];
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FB_PREP_THREADS)
 k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint32_t *nframes,
        int32_t *smp, FbSub *subs, uint8_t *ch_modes)
 {
-    __shared__ uint64_t red[32];
+    __shared__ uint64_t s_sum[FB_PREP_THREADS / 32][4];
+    __shared__ uint32_t s_or[FB_PREP_THREADS / 32][FB_MAX_CH_UNROLL];
+    __shared__ int32_t s_mn[FB_PREP_THREADS / 32][FB_MAX_CH_UNROLL], s_mx[FB_PREP_THREADS / 32][FB_MAX_CH_UNROLL];
     __shared__ int s_mode;
+    __shared__ int s_wasted[FB_MAX_CH_UNROLL];
     const uint32_t f = blockIdx.x;
     if (f >= *nframes) return;
     const FbFrame fr = frames[f];
@@ -201,6 +257,7 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
     const size_t ibase = (size_t)fr.start * (size_t)C;      /* interleaved index of sample 0 */
     int32_t *plane = smp + ibase;
     const int tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nw = (T + 31) >> 5;
 
     /* ---- stereo mode estimate, encode.c:598-643 ---------------------- */
     int mode = 0;                                            /* NOT_STEREO */
@@ -211,33 +268,41 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
             for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
                 int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2];
                 fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
+                /* 32-bit sums inside a run: 8 terms below 2^28 each for inputs of <= 24 bits */
+                uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                const bool whole = i >= 2 && i + FB_PREP_RUN <= n;
 #pragma unroll
                 for (int k = 0; k < FB_PREP_RUN; k++) {
-                    if (i + k < 2 || i + k >= n) continue;
+                    if (!whole && (i + k < 2 || i + k >= n)) continue;
                     const int32_t lt = (int32_t)((uint32_t)lw[k + 2] - 2u * (uint32_t)lw[k + 1] + (uint32_t)lw[k]);
                     const int32_t rt = (int32_t)((uint32_t)rw[k + 2] - 2u * (uint32_t)rw[k + 1] + (uint32_t)rw[k]);
                     const int32_t m = (int32_t)((uint32_t)lt + (uint32_t)rt) >> 1;
                     const int32_t d = (int32_t)((uint32_t)lt - (uint32_t)rt);
-                    s0 += (uint64_t)(int64_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
-                    s1 += (uint64_t)(int64_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
-                    s2 += (uint64_t)(int64_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);
-                    s3 += (uint64_t)(int64_t)(d < 0 ? (int32_t)(0u - (uint32_t)d) : d);
+                    if (cfg.bps <= 24) {
+                        a0 += (uint32_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
+                        a1 += (uint32_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
+                        a2 += (uint32_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);
+                        a3 += (uint32_t)(d < 0 ? (int32_t)(0u - (uint32_t)d) : d);
+                    } else {
+                        s0 += (uint64_t)(int64_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
+                        s1 += (uint64_t)(int64_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
+                        s2 += (uint64_t)(int64_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);
+                        s3 += (uint64_t)(int64_t)(d < 0 ? (int32_t)(0u - (uint32_t)d) : d);
+                    }
                 }
+                s0 += a0; s1 += a1; s2 += a2; s3 += a3;
             }
-            s0 = fb_block_sum_u64(s0, red);
-            s1 = fb_block_sum_u64(s1, red);
-            s2 = fb_block_sum_u64(s2, red);
-            s3 = fb_block_sum_u64(s3, red);
+            s0 = fb_warp_sum_u64(s0); s1 = fb_warp_sum_u64(s1); s2 = fb_warp_sum_u64(s2); s3 = fb_warp_sum_u64(s3);
+            if (lane == 0) { s_sum[warp][0] = s0; s_sum[warp][1] = s1; s_sum[warp][2] = s2; s_sum[warp][3] = s3; }
+            __syncthreads();
             if (tid == 0) {
-                uint64_t s[4] = {s0, s1, s2, s3}, score[4];
+                uint64_t s[4] = {0, 0, 0, 0}, score[4];
+                for (int w = 0; w < nw; w++)
+                    for (int q = 0; q < 4; q++) s[q] += s_sum[w][q];
                 for (int i = 0; i < 4; i++) {
                     /* k from the uint32-truncated search, cost kept in uint64 (encode.c:617-620) */
                     const uint64_t two = 2 * s[i];
-                    int best = 0; uint32_t bb = 0xffffffffu;
-                    for (int k = 0; k <= 30; k++) {
-                        uint32_t b = (uint32_t)fb_rice_count64(two, n, k);
-                        if (b < bb) { bb = b; best = k; }
-                    }
+                    const int best = fb_rice_k(two, n);
                     s[i] = fb_rice_count64(two, n, best);
                 }
                 score[0] = s[0] + s[1]; score[1] = s[0] + s[3];
@@ -252,59 +317,23 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
     }
 
     /* ---- deinterleave + decorrelate, gather plane statistics ----------- */
-    uint32_t orv[FB_MAX_CH_UNROLL], mx[FB_MAX_CH_UNROLL], ne[FB_MAX_CH_UNROLL];
-    int32_t first[FB_MAX_CH_UNROLL];
+    FbPlaneStat st[FB_MAX_CH_UNROLL];
 #pragma unroll
-    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) { orv[c] = 0; mx[c] = 0; ne[c] = 0; first[c] = 0; }
+    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) { st[c].orv = 0; st[c].mn = 0x7fffffff; st[c].mx = (int32_t)0x80000000; }
 
     if (C == 2) {
-        int32_t l = fb_load_pcm(pcm, fmt, ibase), r = fb_load_pcm(pcm, fmt, ibase + 1);
-        if (mode == 10)     { first[0] = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; first[1] = (int32_t)((uint32_t)l - (uint32_t)r); }
-        else if (mode == 8) { first[0] = l; first[1] = (int32_t)((uint32_t)l - (uint32_t)r); }
-        else if (mode == 9) { first[0] = (int32_t)((uint32_t)l - (uint32_t)r); first[1] = r; }
-        else                { first[0] = l; first[1] = r; }
-        const bool planes_aligned = ((((size_t)plane) | ((size_t)n * 4u)) & 15u) == 0;
-        for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
-            int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2], av[FB_PREP_RUN], bv[FB_PREP_RUN];
-            fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
-#pragma unroll
-            for (int k = 0; k < FB_PREP_RUN; k++) {
-                l = lw[k + 2]; r = rw[k + 2];
-                int32_t a, b;
-                if (mode == 10)     { a = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; b = (int32_t)((uint32_t)l - (uint32_t)r); }
-                else if (mode == 8) { a = l; b = (int32_t)((uint32_t)l - (uint32_t)r); }
-                else if (mode == 9) { a = (int32_t)((uint32_t)l - (uint32_t)r); b = r; }
-                else                { a = l; b = r; }
-                av[k] = a; bv[k] = b;
-                if (i + k < n) {
-                    orv[0] |= (uint32_t)a; orv[1] |= (uint32_t)b;
-                    ne[0] |= (uint32_t)(a != first[0]); ne[1] |= (uint32_t)(b != first[1]);
-                    mx[0] = max(mx[0], (uint32_t)(a < 0 ? ~a : a)); mx[1] = max(mx[1], (uint32_t)(b < 0 ? ~b : b));
-                }
-            }
-            if (i + FB_PREP_RUN <= n && planes_aligned) {
-                int4 *pa = reinterpret_cast<int4 *>(plane + i), *pb = reinterpret_cast<int4 *>(plane + n + i);
-                pa[0] = make_int4(av[0], av[1], av[2], av[3]); pa[1] = make_int4(av[4], av[5], av[6], av[7]);
-                pb[0] = make_int4(bv[0], bv[1], bv[2], bv[3]); pb[1] = make_int4(bv[4], bv[5], bv[6], bv[7]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < FB_PREP_RUN; k++)
-                    if (i + k < n) { plane[i + k] = av[k]; plane[n + i + k] = bv[k]; }
-            }
-        }
+        if (mode == 10)     fb_prep_stereo<10>(pcm, fmt, ibase, n, plane, st[0], st[1]);
+        else if (mode == 8) fb_prep_stereo<8>(pcm, fmt, ibase, n, plane, st[0], st[1]);
+        else if (mode == 9) fb_prep_stereo<9>(pcm, fmt, ibase, n, plane, st[0], st[1]);
+        else                fb_prep_stereo<1>(pcm, fmt, ibase, n, plane, st[0], st[1]);
     } else {
-#pragma unroll
-        for (int c = 0; c < FB_MAX_CH_UNROLL; c++)
-            if (c < C) first[c] = fb_load_pcm(pcm, fmt, ibase + c);
         for (int i = tid; i < n; i += T) {
 #pragma unroll
             for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
                 if (c < C) {
-                    int32_t a = fb_load_pcm(pcm, fmt, ibase + (size_t)i * C + c);
+                    const int32_t a = fb_load_pcm(pcm, fmt, ibase + (size_t)i * C + c);
                     plane[(size_t)c * n + i] = a;
-                    orv[c] |= (uint32_t)a;
-                    ne[c] |= (uint32_t)(a != first[c]);
-                    mx[c] = max(mx[c], (uint32_t)(a < 0 ? ~a : a));
+                    st[c].orv |= (uint32_t)a; st[c].mn = min(st[c].mn, a); st[c].mx = max(st[c].mx, a);
                 }
             }
         }
@@ -314,14 +343,44 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
 #pragma unroll
     for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
         if (c < C) {
-            const uint32_t o = fb_block_or_u32(orv[c], red);
-            const uint32_t nz = fb_block_or_u32(ne[c], red);
-            const uint32_t m = fb_block_max_u32(mx[c], red);
-            int wasted = 0;
-            if (o) {
-                wasted = __ffs((int)o) - 1;
-                if (wasted >= cfg.bps - 1) wasted = 0;
-            }
+            const uint32_t o = __reduce_or_sync(FB_FULL_MASK, st[c].orv);
+            const int32_t lo = __reduce_min_sync(FB_FULL_MASK, st[c].mn);
+            const int32_t hi = __reduce_max_sync(FB_FULL_MASK, st[c].mx);
+            if (lane == 0) { s_or[warp][c] = o; s_mn[warp][c] = lo; s_mx[warp][c] = hi; }
+        }
+    }
+    __syncthreads();
+    if (tid < C) {
+        const int c = tid;
+        uint32_t o = 0;
+        int32_t lo = 0x7fffffff, hi = (int32_t)0x80000000;
+        for (int w = 0; w < nw; w++) { o |= s_or[w][c]; lo = min(lo, s_mn[w][c]); hi = max(hi, s_mx[w][c]); }
+        int wasted = 0;
+        if (o) {
+            wasted = __ffs((int)o) - 1;
+            if (wasted >= cfg.bps - 1) wasted = 0;
+        }
+        s_wasted[c] = wasted;
+        /* bound on |sample|: ~v for negative v (two's complement magnitude - 1) */
+        const uint32_t m = max((uint32_t)(hi < 0 ? ~hi : hi), (uint32_t)(lo < 0 ? ~lo : lo));
+        FbSub *sb = &subs[(size_t)f * C + c];
+        int obits = cfg.bps;
+        if ((mode == 10 || mode == 8) && c == 1) obits++;
+        if (mode == 9 && c == 0) obits++;
+        sb->obits = obits - wasted;
+        sb->wasted = wasted;
+        sb->is_const = lo == hi ? 1 : 0;
+        sb->first = lo >> wasted;                    /* read only when is_const: every sample equals lo */
+        sb->maxabs = (m >> wasted) + 1u;
+        sb->type = -1; sb->order = 0; sb->shift = 0; sb->method = 0; sb->porder = 0;
+        sb->est_order = 0; sb->est_bits = 0;
+    }
+    if (tid == 0) ch_modes[f] = (uint8_t)mode;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
+        if (c < C) {
+            const int wasted = s_wasted[c];
             if (wasted) {
                 int32_t *pl = plane + (size_t)c * n;
                 if (C == 2) {                                       /* own elements only: same runs as above */
@@ -331,22 +390,8 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
                     for (int i = tid; i < n; i += T) pl[i] >>= wasted;
                 }
             }
-            if (tid == 0) {
-                FbSub *sb = &subs[(size_t)f * C + c];
-                int obits = cfg.bps;
-                if ((mode == 10 || mode == 8) && c == 1) obits++;
-                if (mode == 9 && c == 0) obits++;
-                sb->obits = obits - wasted;
-                sb->wasted = wasted;
-                sb->is_const = nz ? 0 : 1;
-                sb->first = first[c] >> wasted;
-                sb->maxabs = (m >> wasted) + 1u;         /* bound on |sample| */
-                sb->type = -1; sb->order = 0; sb->shift = 0; sb->method = 0; sb->porder = 0;
-                sb->est_order = 0; sb->est_bits = 0;
-            }
         }
     }
-    if (tid == 0) ch_modes[f] = (uint8_t)mode;
 }
 
 #endif

@@ -201,6 +201,27 @@ inline unsigned __reduce_max_sync(unsigned mask, unsigned v)
     return r;
 }
 
+inline int __reduce_max_sync(unsigned mask, int v)
+{
+    cuemu::WarpState &w = cuemu::my_warp();
+    w.slot[cuemu::lane_id()] = (unsigned)v;
+    cuemu::warp_barrier(mask);
+    int r = INT32_MIN;
+    for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r = std::max(r, (int)(unsigned)w.slot[l]);
+    cuemu::warp_barrier(mask);
+    return r;
+}
+inline int __reduce_min_sync(unsigned mask, int v)
+{
+    cuemu::WarpState &w = cuemu::my_warp();
+    w.slot[cuemu::lane_id()] = (unsigned)v;
+    cuemu::warp_barrier(mask);
+    int r = INT32_MAX;
+    for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r = std::min(r, (int)(unsigned)w.slot[l]);
+    cuemu::warp_barrier(mask);
+    return r;
+}
+
 /* ---- atomics (single OS thread: plain read-modify-write) ------------- */
 template <class T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicOr(T *p, T v)  { T o = *p; *p = o | v; return o; }

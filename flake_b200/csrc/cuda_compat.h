@@ -36,4 +36,37 @@ __device__ __forceinline__ void fb_cp_async_wait_all(void)
 }
 #endif
 
+/* marks a block as not speculatable, so that a rarely taken `if` stays a branch instead of
+ * being turned into selects executed by every thread */
+#ifdef FLAKE_B200_CUDA_EMU
+#define FB_COLD_BLOCK() do { } while (0)
+#else
+#define FB_COLD_BLOCK() asm volatile("" ::: "memory")
+#endif
+
+/* 128-bit load from shared memory at a compile-time byte offset from a shared-space address.
+ * Pointers that reach a function as arguments are generic to the compiler; going through the
+ * 32-bit shared address makes the loads LDS instead of generic LD. */
+#ifdef FLAKE_B200_CUDA_EMU
+typedef const unsigned char *fb_sptr;
+static inline fb_sptr fb_to_sptr(const void *p) { return (const unsigned char *)p; }
+template <int OFF> static inline int4 fb_lds128(fb_sptr a) { int4 v; memcpy(&v, a + OFF, 16); return v; }
+static inline int4 fb_lds128_at(fb_sptr a, int byte_off) { int4 v; memcpy(&v, a + byte_off, 16); return v; }
+#else
+typedef unsigned fb_sptr;
+__device__ __forceinline__ fb_sptr fb_to_sptr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF> __device__ __forceinline__ int4 fb_lds128(fb_sptr a)
+{
+    int4 v;
+    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ int4 fb_lds128_at(fb_sptr a, int byte_off)
+{
+    int4 v;
+    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a + (unsigned)byte_off));
+    return v;
+}
+#endif
+
 #endif

@@ -259,20 +259,46 @@ __device__ __noinline__ void fb_evaluate(FbSearchShared<MAXP> &S, int slot, cons
 /* ------------------------------------------------------------------ */
 /* fast path: block staged in shared memory in a skewed layout          */
 /* ------------------------------------------------------------------ */
-#define FB_RUN 16                 /* consecutive samples per thread and tile */
+#ifndef FB_RUN
+#define FB_RUN 16                 /* consecutive samples per thread and tile: 16 or 8 */
+#endif
 #define FB_HIST 32                /* zero samples in front of sample 0 */
 
-/* logical index (sample i lives at logical i + FB_HIST) -> word offset; every
- * 16-sample run is followed by 4 pad words so that 128-bit loads of threads
- * whose runs are 16 samples apart hit distinct bank groups */
+/* logical index (sample i lives at logical i + FB_HIST) -> word offset.  The 128-bit loads of
+ * eight neighbouring threads must hit the eight distinct 16-byte bank groups:
+ *   runs of 16: 4 pad words after every 16 samples (granule 5t + const);
+ *   runs of 8:  4 pad words after every 32 samples (granule 2t + (2t >> 3) + const). */
+#if FB_RUN == 16
 __host__ __device__ __forceinline__ int fb_skew(int logical) { return logical + ((logical >> 4) << 2); }
-__host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n + FB_HIST + FB_RUN) + 8 + 1) & ~1; }
+#else
+__host__ __device__ __forceinline__ int fb_skew(int logical) { return logical + ((logical >> 5) << 2); }
+#endif
+__host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n + FB_HIST + 16) + 8 + 1) & ~1; }
 /* 64-bit zig-zag sums, one per 16-sample run, per group member: words */
 __host__ __device__ __forceinline__ int fb_runsum_words(int n) { return 2 * (((n + FB_RUN - 1) / FB_RUN) + 2); }
 /* staged plane + the run sums of a whole group, in 32-bit words */
 __host__ __device__ __forceinline__ int fb_search_smem_words(int n) { return fb_skew_words(n) + FB_GROUP * fb_runsum_words(n); }
 /* word offset of logical (16 m + d) relative to that of logical 16 m; d may be negative */
 __host__ __device__ constexpr int fb_skew_delta(int d) { return d + 4 * (d >= 0 ? d / 16 : -((-d + 15) / 16)); }
+
+/* window of a run: groups 0..G-1 of four samples, group g at logical offset 4g - P from the run */
+template <int P, int G> struct FbWindow {
+    /* xr: shared address of the run's first sample (runs of 16) or of the staged plane (runs
+     * of 8, L0 = logical index of the run's first sample) */
+    static __device__ __forceinline__ void load(fb_sptr xr, int L0, int32_t *w)
+    {
+        FbWindow<P, G - 1>::load(xr, L0, w);
+#if FB_RUN == 16
+        const int4 v = fb_lds128<4 * fb_skew_delta(4 * (G - 1) - P)>(xr);
+#else
+        const int4 v = fb_lds128_at(xr, 4 * fb_skew(L0 + 4 * (G - 1) - P));
+#endif
+        w[4 * (G - 1)] = v.x; w[4 * (G - 1) + 1] = v.y; w[4 * (G - 1) + 2] = v.z; w[4 * (G - 1) + 3] = v.w;
+    }
+};
+template <int P> struct FbWindow<P, 0> {
+    static __device__ __forceinline__ void load(fb_sptr, int, int32_t *) {}
+};
 
 #define FB_SUMS  1                /* cost the candidate: zig-zag sums */
 #define FB_STORE 2                /* write the residual to global memory */
@@ -311,18 +337,19 @@ __device__ __noinline__ void fb_run_tail(FbSearchShared<MAXP> &S, const int32_t 
         }
     }
     if (mode & FB_SUMS) {
-        if (runsum) runsum[i0 >> 4] = acc;
+        if (runsum) runsum[i0 / FB_RUN] = acc;
         else if (acc) atomicAdd(&S.sums[pcur], acc);
     }
 }
 
 /* full run whose partitions are not whole runs: walk it, flushing at partition boundaries */
+struct FbRunRegs { int4 g[FB_RUN / 4]; };
+
 template <int MAXP>
-__device__ __noinline__ void fb_run_scatter(FbSearchShared<MAXP> &S, int i0, int order, int psize,
-                                            int4 r0, int4 r1, int4 r2, int4 r3)
+__device__ __noinline__ void fb_run_scatter(FbSearchShared<MAXP> &S, int i0, int order, int psize, FbRunRegs rr)
 {
-    const int32_t r[FB_RUN] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w,
-                               r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+    int32_t r[FB_RUN];
+    for (int g = 0; g < FB_RUN / 4; g++) { r[4 * g] = rr.g[g].x; r[4 * g + 1] = rr.g[g].y; r[4 * g + 2] = rr.g[g].z; r[4 * g + 3] = rr.g[g].w; }
     unsigned long long acc = 0;
     int pcur = -1;
     for (int k = 0; k < FB_RUN; k++) {
@@ -339,12 +366,9 @@ __device__ __noinline__ void fb_run_scatter(FbSearchShared<MAXP> &S, int i0, int
 }
 
 /* full run to a destination that is not 16-byte aligned */
-__device__ __noinline__ void fb_run_store_scalar(int32_t *dst, int4 r0, int4 r1, int4 r2, int4 r3)
+__device__ __noinline__ void fb_run_store_scalar(int32_t *dst, FbRunRegs rr)
 {
-    dst[0] = r0.x; dst[1] = r0.y; dst[2] = r0.z; dst[3] = r0.w;
-    dst[4] = r1.x; dst[5] = r1.y; dst[6] = r1.z; dst[7] = r1.w;
-    dst[8] = r2.x; dst[9] = r2.y; dst[10] = r2.z; dst[11] = r2.w;
-    dst[12] = r3.x; dst[13] = r3.y; dst[14] = r3.z; dst[15] = r3.w;
+    for (int g = 0; g < FB_RUN / 4; g++) { dst[4 * g] = rr.g[g].x; dst[4 * g + 1] = rr.g[g].y; dst[4 * g + 2] = rr.g[g].z; dst[4 * g + 3] = rr.g[g].w; }
 }
 
 /*
@@ -367,12 +391,12 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const i
     const int shift = S.shift[row];
 
     int32_t w[P + FB_RUN];
-    const int32_t *xr = xs + fb_skew(i0 + FB_HIST);           /* i0 + FB_HIST is a multiple of 16 */
-#pragma unroll
-    for (int g = 0; g < (P + FB_RUN) / 4; g++) {
-        const int4 v = *reinterpret_cast<const int4 *>(xr + fb_skew_delta(4 * g - P));
-        w[4 * g] = v.x; w[4 * g + 1] = v.y; w[4 * g + 2] = v.z; w[4 * g + 3] = v.w;
-    }
+#if FB_RUN == 16
+    const fb_sptr xr = fb_to_sptr(xs + fb_skew(i0 + FB_HIST));  /* i0 + FB_HIST is a multiple of 16 */
+#else
+    const fb_sptr xr = fb_to_sptr(xs);
+#endif
+    FbWindow<P, (P + FB_RUN) / 4>::load(xr, i0 + FB_HIST, w);
 
     /* residuals of the run, branch free */
     int32_t r[FB_RUN];
@@ -404,8 +428,10 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const i
         }
     }
     if (i0 < order) {                                         /* warm-up samples pass through, uncounted */
+        FB_COLD_BLOCK();
+        /* order <= P: beyond the first run only orders above 16 have warm-up samples */
 #pragma unroll
-        for (int k = 0; k < FB_RUN; k++) {
+        for (int k = 0; k < (P < FB_RUN ? P : FB_RUN); k++) {
             if (i0 + k < order) {
                 if (MODE & FB_SUMS) acc -= fb_zigzag(r[k]);
                 r[k] = w[P + k];
@@ -419,17 +445,23 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const i
             for (int g = 0; g < FB_RUN / 4; g++)
                 reinterpret_cast<int4 *>(dst)[g] = make_int4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         } else {
-            fb_run_store_scalar(dst, make_int4(r[0], r[1], r[2], r[3]), make_int4(r[4], r[5], r[6], r[7]),
-                                make_int4(r[8], r[9], r[10], r[11]), make_int4(r[12], r[13], r[14], r[15]));
+            FbRunRegs rr;
+#pragma unroll
+            for (int g = 0; g < FB_RUN / 4; g++) rr.g[g] = make_int4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+            fb_run_store_scalar(dst, rr);
         }
     }
     if (MODE & FB_SUMS) {
         /* partitions that are whole multiples of the run length (the rule for every
          * power-of-two block size): one sum per run, folded into the partition sums by the
          * finishing warp -- no atomics on the hot loop */
-        if (runsum) runsum[i0 >> 4] = acc;
-        else fb_run_scatter<MAXP>(S, i0, order, psize, make_int4(r[0], r[1], r[2], r[3]), make_int4(r[4], r[5], r[6], r[7]),
-                                  make_int4(r[8], r[9], r[10], r[11]), make_int4(r[12], r[13], r[14], r[15]));
+        if (runsum) runsum[i0 / FB_RUN] = acc;
+        else {
+            FbRunRegs rr;
+#pragma unroll
+            for (int g = 0; g < FB_RUN / 4; g++) rr.g[g] = make_int4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+            fb_run_scatter<MAXP>(S, i0, order, psize, rr);
+        }
     }
 }
 
@@ -599,7 +631,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         for (int i = 4 * tid; i < n4; i += 4 * T) fb_cp_async16(xs + fb_skew(i + FB_HIST), xg + i);
 #pragma unroll 8
         for (int i = n4 + tid; i < n; i += T) xs[fb_skew(i + FB_HIST)] = xg[i];
-        for (int i = n + tid; i < n + FB_RUN; i += T) xs[fb_skew(i + FB_HIST)] = 0;
+        for (int i = n + tid; i < n + 16; i += T) xs[fb_skew(i + FB_HIST)] = 0;
     }
 
     int min_order = cfg.min_order, max_order = cfg.max_order;

@@ -268,7 +268,8 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
             for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
                 int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2];
                 fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
-                /* 32-bit sums inside a run: 8 terms below 2^28 each for inputs of <= 24 bits */
+                /* 32-bit sums inside a run: 8 terms below 2^28 each when the packed format bounds
+                 * the samples to 24 bits; int32 input may hold anything and is summed in 64 bits */
                 uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
                 const bool whole = i >= 2 && i + FB_PREP_RUN <= n;
 #pragma unroll
@@ -278,7 +279,7 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
                     const int32_t rt = (int32_t)((uint32_t)rw[k + 2] - 2u * (uint32_t)rw[k + 1] + (uint32_t)rw[k]);
                     const int32_t m = (int32_t)((uint32_t)lt + (uint32_t)rt) >> 1;
                     const int32_t d = (int32_t)((uint32_t)lt - (uint32_t)rt);
-                    if (cfg.bps <= 24) {
+                    if (fmt != FB_PCM_S32) {
                         a0 += (uint32_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
                         a1 += (uint32_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
                         a2 += (uint32_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);

@@ -585,7 +585,7 @@ __device__ __forceinline__ void fb_store_residual(FbSearchShared<MAXP> &S, const
 }
 
 #ifndef FB_SEARCH_MINBLOCKS
-#define FB_SEARCH_MINBLOCKS 1
+#define FB_SEARCH_MINBLOCKS 5    /* <= 102 registers: five CTAs per SM; 4 and 6 measured slower */
 #endif
 
 template <int MAXP>

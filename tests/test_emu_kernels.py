@@ -126,3 +126,32 @@ def test_crc_combination_algebra(emu_lib, oracle):
         ca, cb = L.orc_crc16(a, len(a)), L.orc_crc16(b, len(b))
         m = emu_lib.fb_test_gf16_xpow8(len(b))
         assert emu_lib.fb_test_gf16_mul(ca, m) ^ cb == L.orc_crc16(a + b, len(a) + len(b))
+
+
+# Order-search control flow of k_search: candidates are costed in groups and the searches of
+# optimize.c:205-261 replayed on the stored totals; the group planner of the log search merges
+# steps whose candidate sets do not depend on pending results.  Sweep the (method, min, max)
+# space, tileable and non-tileable block sizes.
+ORDER_SWEEP = [(om, lo, hi, bs)
+               for om in (2, 3, 4, 5, 6)
+               for (lo, hi) in ((1, 12), (1, 8), (3, 9), (5, 5), (1, 32), (8, 32), (2, 3), (1, 2), (12, 12), (7, 20), (1, 17))
+               for bs in (1024, 576)]
+
+
+@pytest.mark.parametrize("om,lo,hi,bs", ORDER_SWEEP, ids=["om%d_%d_%d_bs%d" % c for c in ORDER_SWEEP])
+def test_order_search_sweep(om, lo, hi, bs, emu_lib, oracle):
+    ov = {"order_method": om, "min_prediction_order": lo, "max_prediction_order": hi, "block_size": bs,
+          "prediction_type": 2, "variable_block_size": 0}
+    pcm = synth.synth_pcm(bs * 2 + 40, 2, 16, 44100, seed=om * 100 + lo * 7 + hi, kind="mix")
+    got = api.encode_batch(emu_lib, pcm, 44100, 16, 8, chunk_blocks=4, **ov)
+    want, flen, fbs, mx = oracle.encode_stream(pcm, 44100, 16, 8, **ov)
+    assert got.payload == want
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 4), (0, 0), (2, 4), (1, 3), (4, 4)])
+def test_fixed_order_sweep(lo, hi, emu_lib, oracle):
+    ov = {"prediction_type": 1, "min_prediction_order": lo, "max_prediction_order": hi, "block_size": 1152}
+    pcm = synth.synth_pcm(1152 * 2 + 9, 2, 16, 44100, seed=lo * 5 + hi, kind="mix")
+    got = api.encode_batch(emu_lib, pcm, 44100, 16, 2, chunk_blocks=4, **ov)
+    want, flen, fbs, mx = oracle.encode_stream(pcm, 44100, 16, 2, **ov)
+    assert got.payload == want

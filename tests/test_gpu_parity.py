@@ -119,3 +119,29 @@ def test_matches_compiled_reference(gpu_lib, oracle):
         want = api.encode_per_block(ref, pcm, rate, bps, level)
         got = api.encode_batch(gpu_lib, pcm, rate, bps, level)
         assert got.file_bytes() == want.file_bytes()
+
+
+# order-search control flow (candidate groups + replay, see tests/test_emu_kernels.py) on the device
+ORDER_SWEEP = [(6, 1, 12, 4096), (6, 1, 8, 4096), (6, 3, 9, 1024), (6, 1, 32, 4096), (6, 8, 32, 2048), (6, 7, 20, 576),
+               (6, 1, 2, 4608), (6, 12, 12, 4096), (5, 1, 12, 4096), (5, 1, 32, 1024), (5, 5, 5, 576), (4, 1, 12, 4096),
+               (4, 1, 32, 4608), (3, 1, 12, 4096), (3, 2, 3, 1024), (2, 1, 12, 4096), (2, 8, 32, 4096)]
+
+
+@pytest.mark.parametrize("om,lo,hi,bs", ORDER_SWEEP, ids=["om%d_%d_%d_bs%d" % c for c in ORDER_SWEEP])
+def test_order_search_sweep(om, lo, hi, bs, gpu_lib, oracle):
+    ov = {"order_method": om, "min_prediction_order": lo, "max_prediction_order": hi, "block_size": bs,
+          "prediction_type": 2, "variable_block_size": 0}
+    pcm = synth.synth_pcm(bs * 5 + 40, 2, 16, 44100, seed=om * 100 + lo * 7 + hi, kind="mix")
+    got = api.encode_batch(gpu_lib, pcm, 44100, 16, 8, chunk_blocks=4, **ov)
+    want, flen, fbs, mx = oracle.encode_stream(pcm, 44100, 16, 8, **ov)
+    assert got.payload == want
+
+
+def test_int32_input_beyond_24_bits_estimate_is_exact(gpu_lib, oracle):
+    """The stereo estimate sums in 32 bits per run only for the packed formats; int32 input that
+    exceeds its declared width must still give the reference's decision (64-bit sums)."""
+    pcm = synth.synth_pcm(4096 * 2, 2, 16, 44100, seed=9)
+    pcm[100:3000, 0] = (pcm[100:3000, 0].astype(np.int64) * 30000).clip(-2**31 + 1, 2**31 - 1).astype(np.int32)
+    got = api.encode_batch(gpu_lib, pcm, 44100, 16, 8, chunk_blocks=2)
+    want, flen, fbs, mx = oracle.encode_stream(pcm, 44100, 16, 8)
+    assert got.payload == want

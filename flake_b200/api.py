@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(_HERE, "lib", "libflake.so")
 
 PCM_S32, PCM_S16LE, PCM_S24LE, PCM_S8 = 0, 1, 2, 3
 
-STAGES = ("frames", "prep", "lpc", "search", "pack", "offsets", "compact")
+STAGES = ("frames", "prep", "lpc", "search", "pack")
 
 ORDER_METHOD = {"max": 0, "est": 1, "2level": 2, "4level": 3, "8level": 4, "search": 5, "log": 6}
 

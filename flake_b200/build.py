@@ -65,7 +65,8 @@ def build_product(force: bool = False, variant: str = "", defines=()) -> str:
               "-c", os.path.join(CSRC, c), "-o", o])
         objs.append(o)
     _run([nvcc, "-shared", "-o", out] + objs +
-         ["-Xlinker", "-Bsymbolic", "-cudart", "static", "-lpthread"])
+         ["-Xlinker", "-Bsymbolic", "-Xlinker", "--version-script=" + os.path.join(CSRC, "libflake.map"),
+          "-cudart", "static", "-lpthread"])
     return out
 
 

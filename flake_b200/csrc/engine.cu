@@ -7,9 +7,9 @@
  *   k_prep      per frame      ingest, stereo decision, wasted bits, constant test
  *   k_lpc       per subframe   FP64 window/autocorrelation/Levinson/quantise
  *   k_search    per subframe   order + Rice search, final residual
- *   k_pack      per frame      bit packing, CRC-8/16, verbatim size check
- *   k_offsets   1 CTA          exclusive scan of frame lengths, chunk summary
- *   k_compact   per frame      staged slots -> contiguous output
+ *   k_pack      per frame      bit packing, CRC-8/16, verbatim size check, offsets by a
+ *                              decoupled look-back over the frame lengths, frames written
+ *                              back to back into the output, chunk summary
  */
 #include "cuda_compat.h"
 #include "engine.h"
@@ -44,6 +44,7 @@ struct FbEngine {
     uint32_t *d_vbs_sizes, *d_vbs_counts;
     uint16_t *d_xpow32;             /* x^(32 j) mod P, CRC-16 chunk merge (k_pack) */
     uint32_t *d_crc16tab;           /* CRC-16 slicing tables [4][256] uint16 (k_pack) */
+    unsigned long long *d_status;   /* look-back status per frame (k_pack) */
     int search_smem_ints, pack_smem_words;
     uint64_t launches;
     /* optional per-kernel CUDA-event timing (bench.py roofline) */
@@ -115,6 +116,7 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     FB_TRY_ALLOC(e->d_slots, e->slot_bytes);
     FB_TRY_ALLOC(e->d_frame_len, sizeof(uint32_t) * (size_t)e->max_frames);
     FB_TRY_ALLOC(e->d_frame_off, sizeof(uint64_t) * (size_t)e->max_frames);
+    FB_TRY_ALLOC(e->d_status, sizeof(unsigned long long) * (size_t)e->max_frames);
     if (cfg->prediction_type == 2) {
         FB_TRY_ALLOC(e->d_coefs, sizeof(int32_t) * FB_MAX_ORDER * FB_MAX_ORDER * (size_t)e->max_subs);
         FB_TRY_ALLOC(e->d_shifts, sizeof(int32_t) * FB_MAX_ORDER * (size_t)e->max_subs);
@@ -178,7 +180,7 @@ extern "C" void fb_engine_destroy(FbEngine *e)
     cudaFree(e->d_frames); cudaFree(e->d_nframes); cudaFree(e->d_subs); cudaFree(e->d_modes);
     cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
     cudaFree(e->d_win); cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
-    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32); cudaFree(e->d_crc16tab);
+    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32); cudaFree(e->d_crc16tab); cudaFree(e->d_status);
     if (e->tev[0][0])
         for (int p = 0; p < FB_TIMING_RING; p++)
             for (int i = 0; i <= FB_NUM_STAGES; i++) cudaEventDestroy(e->tev[p][i]);
@@ -218,7 +220,9 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
         tev = e->tev[e->timing_passes++];
     }
 #define FB_MARK(i) do { if (tev) cudaEventRecord(tev[(i)], st); } while (0)
-    cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st);
+    cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st);          /* frame count, -, pack ticket, - */
+    cudaMemsetAsync(e->d_status, 0, sizeof(unsigned long long) * (size_t)grid_frames, st);
+    cudaMemsetAsync(d_summary, 0, sizeof(FbSummary), st);
     FB_MARK(0);
     if (cfg.variable_block_size) {
         FB_LAUNCH(k_vbs_split, dim3(nblocks), dim3(FB_PREP_THREADS), 0, st,
@@ -264,16 +268,11 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     FB_MARK(4);
     FB_LAUNCH(k_pack, dim3(grid_frames), dim3(FB_PACK_THREADS), (size_t)e->pack_smem_words * 4, st,
               cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
-              flen, d_frame_bs, e->d_verbatim, e->pack_smem_words, e->d_xpow32, e->d_crc16tab);
+              flen, d_frame_bs, e->pack_smem_words, e->d_xpow32, e->d_crc16tab,
+              e->d_nframes + 2, e->d_status, e->d_frame_off, (uint8_t *)d_out, d_summary);
     FB_MARK(5);
-    FB_LAUNCH(k_offsets, dim3(1), dim3(1024), 0, st,
-              e->d_nframes, flen, e->d_frame_off, d_summary, e->d_verbatim);
-    FB_MARK(6);
-    FB_LAUNCH(k_compact, dim3(grid_frames), dim3(256), 0, st,
-              e->d_frames, e->d_nframes, flen, e->d_frame_off, e->d_slots, (uint8_t *)d_out);
-    FB_MARK(7);
 #undef FB_MARK
-    e->launches += 4;
+    e->launches += 2;
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) {
         snprintf(e->err, sizeof e->err, "kernel launch failed: %s", cudaGetErrorString(ce));
@@ -295,7 +294,7 @@ extern "C" int fb_engine_set_timing(FbEngine *e, int on)
 }
 
 /* Fold the recorded passes into the per-stage totals; optionally copy them out.
- * Stages: 0 frame table (+VBS split), 1 prep, 2 lpc, 3 search, 4 pack, 5 offsets, 6 compact. */
+ * Stages: 0 frame table (+VBS split), 1 prep, 2 lpc, 3 search, 4 pack. */
 extern "C" int fb_engine_collect_timing(FbEngine *e, double *ms, uint64_t *launches)
 {
     if (!e) return -1;

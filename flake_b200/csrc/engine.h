@@ -100,8 +100,8 @@ int fb_engine_read_subframes(FbEngine *e, FbSub *host, uint32_t max, void *strea
 
 /* per-stage CUDA-event timing (events recorded on the launching stream between
  * the kernels of a pass).  Stages: 0 frame table (+VBS split), 1 prep, 2 lpc,
- * 3 search, 4 pack, 5 offsets, 6 compact. */
-#define FB_NUM_STAGES 7
+ * 3 search, 4 pack (bit packing, offsets by look-back, frames written in place). */
+#define FB_NUM_STAGES 5
 int  fb_engine_set_timing(FbEngine *e, int on);
 int  fb_engine_collect_timing(FbEngine *e, double *ms, uint64_t *launches);
 void fb_engine_reset_timing(FbEngine *e);

@@ -1,7 +1,8 @@
 /*
  * k_pack.cuh -- parallel frame packer, one CTA per frame (encode.c:700-977,
- * bitio.h, crc.c) plus the compaction of the staged frames into one
- * contiguous byte stream.
+ * bitio.h, crc.c).  Frames leave the kernel back to back in one contiguous byte
+ * stream: their offsets come from a decoupled look-back over the frame lengths
+ * (single-pass scan), so a frame is written once, straight to its final place.
  *
  * The reference writes a frame serially through a 32-bit accumulator.  Here
  * every thread owns a contiguous run of samples of a subframe: it sizes its
@@ -160,24 +161,38 @@ __device__ __forceinline__ FbSubLayout fb_sub_layout(const FbSub *sb, int n, boo
  * global slot directly).  xpow32[j] = x^(32 j) mod P for the CRC-16 merge;
  * crc16_tables = the four 256-entry slicing tables (uint16, packed in words).
  */
+#define FB_SCAN_AGG    (1ull << 62)      /* status = this frame's length */
+#define FB_SCAN_PREFIX (2ull << 62)      /* status = sum of the lengths up to and including this frame */
+#define FB_SCAN_VALUE  ((1ull << 62) - 1)
+
+/*
+ * ticket / status: zeroed before the launch.  Frames are taken in ticket order (not blockIdx
+ * order), so every frame a CTA looks back at belongs to a CTA that is already running or done.
+ */
 __global__ void __launch_bounds__(FB_PACK_THREADS)
 k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
        const int32_t *res, FbSub *subs, const uint8_t *ch_modes, uint8_t *slots,
-       uint32_t *frame_len, uint32_t *frame_bs, uint32_t *verbatim_count, int smem_words,
-       const uint16_t *xpow32, const uint32_t *crc16_tables)
+       uint32_t *frame_len, uint32_t *frame_bs, int smem_words,
+       const uint16_t *xpow32, const uint32_t *crc16_tables,
+       uint32_t *ticket, unsigned long long *status, uint64_t *frame_off, uint8_t *out, FbSummary *summary)
 {
     FB_DYN_SMEM(dyn);
+    __shared__ uint32_t s_ticket;
+    __shared__ unsigned long long s_off;
     __shared__ uint32_t scan_scratch[33];
     __shared__ __align__(16) uint16_t crc_tab[4][256];
     __shared__ uint32_t s_hdr_len;
     __shared__ uint8_t s_hdr[24];
-    __shared__ uint8_t s_params[256];
+    __shared__ uint8_t s_params[FB_MAX_CH_UNROLL][256];
 
-    const uint32_t f = blockIdx.x;
-    if (f >= *nframes) return;
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t f = s_ticket;
+    const uint32_t nf = *nframes;
+    if (f >= nf) return;
     const FbFrame fr = frames[f];
     const int n = (int)fr.n, C = cfg.channels;
-    const int tid = threadIdx.x, T = blockDim.x;
     const int vsize = fb_verbatim_size(cfg, n);
     /* staging capacity: verbatim encoding plus header slack, see fb_slot_offset */
     const uint32_t cap_bytes = 64u + (uint32_t)(((uint64_t)n * (uint64_t)(C * cfg.bps + 1) + 7u) >> 3);
@@ -232,33 +247,33 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     const int R = (n + T - 1) / T;                  /* samples per thread run */
     const int i0 = min(n, tid * R), i1 = min(n, i0 + R);
 
+    /* ---- phase A: size every subframe -----------------------------------------------------
+     * Per channel: bits of my run, CTA exclusive scan.  The frame length is known after this
+     * phase (a second, trivial round if the frame has to fall back to VERBATIM subframes,
+     * encode.c:949-964), so it is published for the look-back of the following frames before
+     * a single bit is written. */
+    uint32_t myoff[FB_MAX_CH_UNROLL];                /* bit offset of my run inside its subframe's tokens */
+    uint64_t chbit[FB_MAX_CH_UNROLL];                /* first bit of each subframe */
     uint64_t total_bits = 0;
     bool verbatim = false;
     for (int pass = 0; pass < 2; pass++) {
-        if (pass) {                                  /* second try: start from a clean buffer */
-            for (uint32_t w = tid; w < capw; w += T) wbuf[w] = 0;
-            __syncthreads();
-        }
         uint64_t bitpos = (uint64_t)hdr_len * 8u;
-        if (tid == 0) {
-            FbBitPut b; fb_bp_init(b, wbuf, capw, 0);
-            for (uint32_t i = 0; i < hdr_len; i++) fb_bp_put(b, 8, s_hdr[i]);
-            fb_bp_finish(b);
-        }
         for (int c = 0; c < C; c++) {
             const FbSub *sb = &subs[(size_t)f * C + c];
             const FbSubLayout L = fb_sub_layout(sb, n, verbatim);
             const size_t off = (size_t)fr.start * C + (size_t)c * n;
             const int32_t *data = (L.type == 1 || L.type == 0) ? smp + off : res + off;
             const bool rice = (L.type == 8 || L.type == 32);
+            uint8_t *kp = s_params[c];
 
             /* Rice parameters of this subframe into shared memory */
-            if (rice) for (int j = tid; j < (1 << L.porder); j += T) s_params[j] = sb->params[j];
-            __syncthreads();
-
-            /* size my run, then scan.  The partition index is tracked incrementally; 16 samples
-             * that lie in one partition and start 16-byte aligned are taken with four 128-bit
-             * loads and one Rice parameter */
+            if (rice) {
+                for (int j = tid; j < (1 << L.porder); j += T) kp[j] = sb->params[j];
+                __syncthreads();
+            }
+            /* The partition index is tracked incrementally; 16 samples that lie in one
+             * partition and start 16-byte aligned are taken with four 128-bit loads and one
+             * Rice parameter */
             const int jbeg = rice ? max(i0, L.order) : i0;
             uint32_t mybits = 0;
             if (L.type == 1) {
@@ -267,10 +282,10 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
                 int i = jbeg;
                 int p = i / L.psize;
                 int nb = (p + 1) * L.psize;
-                uint32_t k = s_params[p];
+                uint32_t k = kp[p];
                 if (p > 0 && i == p * L.psize) mybits += (uint32_t)L.pbits;
                 while (i < i1) {
-                    if (i == nb) { p++; nb += L.psize; k = s_params[p]; mybits += (uint32_t)L.pbits; }
+                    if (i == nb) { p++; nb += L.psize; k = kp[p]; mybits += (uint32_t)L.pbits; }
                     if (i + 16 <= min(i1, nb) && (((size_t)(data + i)) & 15u) == 0) {
                         const int4 *src = reinterpret_cast<const int4 *>(data + i);
                         const int4 a = src[0], b = src[1], c4 = src[2], d = src[3];
@@ -287,99 +302,114 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
                 }
             }
             uint32_t sub_tokens;
-            const uint32_t myoff = fb_block_exscan_u32(mybits, scan_scratch, &sub_tokens);
-
-            /* preamble: fixed-width fields at known offsets, one writer per field
-             * (every field is <= 32 bits, so both words it can touch are merged atomically) */
-            {
-                const uint64_t pre0 = bitpos + 8u + (uint32_t)L.wasted;          /* after the subframe header */
-                if (tid == 0) {
-                    FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos);
-                    int code = L.type;
-                    if (L.type == 8) code = 8 | L.order;
-                    if (L.type == 32) code = 32 | (L.order - 1);
-                    fb_bp_put(b, 7, (uint32_t)code);         /* leading 0 + 6-bit type */
-                    if (L.wasted) { fb_bp_put(b, 1, 1); fb_bp_skip(b, (uint32_t)(L.wasted - 1)); fb_bp_put(b, 1, 1); }
-                    else fb_bp_put(b, 1, 0);
-                    if (L.type == 0) fb_bp_put_signed(b, L.obits, sb->first);
-                    fb_bp_finish(b);
-                    if (rice) {
-                        uint64_t at = pre0 + (uint64_t)(L.order * L.obits);
-                        if (L.type == 32) {
-                            fb_bp_init(b, wbuf, capw, at);
-                            fb_bp_put(b, 4, 14);
-                            fb_bp_put_signed(b, 5, L.shift);
-                            fb_bp_finish(b);
-                            at += 9u + (uint64_t)L.order * 15u;
-                        }
-                        fb_bp_init(b, wbuf, capw, at);
-                        fb_bp_put(b, 2, (uint32_t)L.method);
-                        fb_bp_put(b, 4, (uint32_t)L.porder);
-                        fb_bp_put(b, (uint32_t)L.pbits, s_params[0]);
-                        fb_bp_finish(b);
-                    }
-                } else if (rice && tid >= 32 && tid < 32 + L.order) {              /* warm-up samples */
-                    const int i = tid - 32;
-                    FbBitPut b; fb_bp_init(b, wbuf, capw, pre0 + (uint64_t)(i * L.obits));
-                    fb_bp_put_signed(b, L.obits, data[i]);
-                    fb_bp_finish(b);
-                } else if (L.type == 32 && tid >= 64 && tid < 64 + L.order) {      /* LPC coefficients */
-                    const int i = tid - 64;
-                    FbBitPut b; fb_bp_init(b, wbuf, capw, pre0 + (uint64_t)(L.order * L.obits) + 9u + (uint64_t)i * 15u);
-                    fb_bp_put_signed(b, 15, sb->coefs[i]);
-                    fb_bp_finish(b);
-                }
-            }
-            /* my tokens */
-            if (mybits) {
-                FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos + L.preamble_bits + myoff);
-                if (L.type == 1) {
-                    for (int i = i0; i < i1; i++) fb_bp_put_signed(b, L.obits, data[i]);
-                } else {
-                    int i = jbeg;
-                    int p = i / L.psize;
-                    int nb = (p + 1) * L.psize;
-                    uint32_t k = s_params[p];
-                    if (p > 0 && i == p * L.psize) fb_bp_put(b, (uint32_t)L.pbits, k);
-                    while (i < i1) {
-                        if (i == nb) { p++; nb += L.psize; k = s_params[p]; fb_bp_put(b, (uint32_t)L.pbits, k); }
-                        if (i + 16 <= min(i1, nb) && (((size_t)(data + i)) & 15u) == 0) {
-                            const int4 *src = reinterpret_cast<const int4 *>(data + i);
-                            const int4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
-                            fb_bp_put_rice(b, fb_zigzag(v0.x), k); fb_bp_put_rice(b, fb_zigzag(v0.y), k);
-                            fb_bp_put_rice(b, fb_zigzag(v0.z), k); fb_bp_put_rice(b, fb_zigzag(v0.w), k);
-                            fb_bp_put_rice(b, fb_zigzag(v1.x), k); fb_bp_put_rice(b, fb_zigzag(v1.y), k);
-                            fb_bp_put_rice(b, fb_zigzag(v1.z), k); fb_bp_put_rice(b, fb_zigzag(v1.w), k);
-                            fb_bp_put_rice(b, fb_zigzag(v2.x), k); fb_bp_put_rice(b, fb_zigzag(v2.y), k);
-                            fb_bp_put_rice(b, fb_zigzag(v2.z), k); fb_bp_put_rice(b, fb_zigzag(v2.w), k);
-                            fb_bp_put_rice(b, fb_zigzag(v3.x), k); fb_bp_put_rice(b, fb_zigzag(v3.y), k);
-                            fb_bp_put_rice(b, fb_zigzag(v3.z), k); fb_bp_put_rice(b, fb_zigzag(v3.w), k);
-                            i += 16;
-                        } else {
-                            fb_bp_put_rice(b, fb_zigzag(data[i]), k);
-                            i++;
-                        }
-                    }
-                }
-                fb_bp_finish(b);
-            }
+            myoff[c] = fb_block_exscan_u32(mybits, scan_scratch, &sub_tokens);
+            chbit[c] = bitpos;
             bitpos += (uint64_t)L.preamble_bits + sub_tokens;
-            __syncthreads();                         /* s_params is re-used by the next channel */
         }
         total_bits = bitpos;
-        const uint64_t nbytes = ((total_bits + 7u) >> 3) + 2u;
         /* encode.c:949: eof (buffer = 3/2 verbatim size) or larger than the verbatim bound */
-        if (pass == 0 && nbytes > (uint64_t)vsize) {
-            verbatim = true;
-            __syncthreads();
-            continue;
-        }
+        if (pass == 0 && ((total_bits + 7u) >> 3) + 2u > (uint64_t)vsize) { verbatim = true; continue; }
         break;
     }
-    __syncthreads();
 
     uint32_t body = (uint32_t)((total_bits + 7u) >> 3);      /* bytes before the CRC-16 */
     if (body + 2u > cap_bytes) body = cap_bytes - 2u;         /* cannot happen for <= 24-bit input */
+    const uint32_t nbytes = body + 2u;
+    if (tid == 0)
+        *(volatile unsigned long long *)&status[f] = (f ? FB_SCAN_AGG : FB_SCAN_PREFIX) | (unsigned long long)nbytes;
+
+    /* ---- phase B: write the bits (no barrier between the subframes) -------------------------- */
+    if (tid == 0) {
+        FbBitPut b; fb_bp_init(b, wbuf, capw, 0);
+        for (uint32_t i = 0; i < hdr_len; i++) fb_bp_put(b, 8, s_hdr[i]);
+        fb_bp_finish(b);
+    }
+    for (int c = 0; c < C; c++) {
+        const FbSub *sb = &subs[(size_t)f * C + c];
+        const FbSubLayout L = fb_sub_layout(sb, n, verbatim);
+        const size_t off = (size_t)fr.start * C + (size_t)c * n;
+        const int32_t *data = (L.type == 1 || L.type == 0) ? smp + off : res + off;
+        const bool rice = (L.type == 8 || L.type == 32);
+        const uint8_t *kp = s_params[c];
+        const uint64_t bitpos = chbit[c];
+        const int jbeg = rice ? max(i0, L.order) : i0;
+
+        /* preamble: fixed-width fields at known offsets, one writer per field
+         * (every field is <= 32 bits, so both words it can touch are merged atomically) */
+        {
+            const uint64_t pre0 = bitpos + 8u + (uint32_t)L.wasted;          /* after the subframe header */
+            if (tid == 0) {
+                FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos);
+                int code = L.type;
+                if (L.type == 8) code = 8 | L.order;
+                if (L.type == 32) code = 32 | (L.order - 1);
+                fb_bp_put(b, 7, (uint32_t)code);         /* leading 0 + 6-bit type */
+                if (L.wasted) { fb_bp_put(b, 1, 1); fb_bp_skip(b, (uint32_t)(L.wasted - 1)); fb_bp_put(b, 1, 1); }
+                else fb_bp_put(b, 1, 0);
+                if (L.type == 0) fb_bp_put_signed(b, L.obits, sb->first);
+                fb_bp_finish(b);
+                if (rice) {
+                    uint64_t at = pre0 + (uint64_t)(L.order * L.obits);
+                    if (L.type == 32) {
+                        fb_bp_init(b, wbuf, capw, at);
+                        fb_bp_put(b, 4, 14);
+                        fb_bp_put_signed(b, 5, L.shift);
+                        fb_bp_finish(b);
+                        at += 9u + (uint64_t)L.order * 15u;
+                    }
+                    fb_bp_init(b, wbuf, capw, at);
+                    fb_bp_put(b, 2, (uint32_t)L.method);
+                    fb_bp_put(b, 4, (uint32_t)L.porder);
+                    fb_bp_put(b, (uint32_t)L.pbits, kp[0]);
+                    fb_bp_finish(b);
+                }
+            } else if (rice && tid >= 32 && tid < 32 + L.order) {              /* warm-up samples */
+                const int i = tid - 32;
+                FbBitPut b; fb_bp_init(b, wbuf, capw, pre0 + (uint64_t)(i * L.obits));
+                fb_bp_put_signed(b, L.obits, data[i]);
+                fb_bp_finish(b);
+            } else if (L.type == 32 && tid >= 64 && tid < 64 + L.order) {      /* LPC coefficients */
+                const int i = tid - 64;
+                FbBitPut b; fb_bp_init(b, wbuf, capw, pre0 + (uint64_t)(L.order * L.obits) + 9u + (uint64_t)i * 15u);
+                fb_bp_put_signed(b, 15, sb->coefs[i]);
+                fb_bp_finish(b);
+            }
+        }
+        /* my tokens */
+        if ((L.type == 1 && i0 < i1) || (rice && jbeg < i1)) {
+            FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos + L.preamble_bits + myoff[c]);
+            if (L.type == 1) {
+                for (int i = i0; i < i1; i++) fb_bp_put_signed(b, L.obits, data[i]);
+            } else {
+                int i = jbeg;
+                int p = i / L.psize;
+                int nb = (p + 1) * L.psize;
+                uint32_t k = kp[p];
+                if (p > 0 && i == p * L.psize) fb_bp_put(b, (uint32_t)L.pbits, k);
+                while (i < i1) {
+                    if (i == nb) { p++; nb += L.psize; k = kp[p]; fb_bp_put(b, (uint32_t)L.pbits, k); }
+                    if (i + 16 <= min(i1, nb) && (((size_t)(data + i)) & 15u) == 0) {
+                        const int4 *src = reinterpret_cast<const int4 *>(data + i);
+                        const int4 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+                        fb_bp_put_rice(b, fb_zigzag(v0.x), k); fb_bp_put_rice(b, fb_zigzag(v0.y), k);
+                        fb_bp_put_rice(b, fb_zigzag(v0.z), k); fb_bp_put_rice(b, fb_zigzag(v0.w), k);
+                        fb_bp_put_rice(b, fb_zigzag(v1.x), k); fb_bp_put_rice(b, fb_zigzag(v1.y), k);
+                        fb_bp_put_rice(b, fb_zigzag(v1.z), k); fb_bp_put_rice(b, fb_zigzag(v1.w), k);
+                        fb_bp_put_rice(b, fb_zigzag(v2.x), k); fb_bp_put_rice(b, fb_zigzag(v2.y), k);
+                        fb_bp_put_rice(b, fb_zigzag(v2.z), k); fb_bp_put_rice(b, fb_zigzag(v2.w), k);
+                        fb_bp_put_rice(b, fb_zigzag(v3.x), k); fb_bp_put_rice(b, fb_zigzag(v3.y), k);
+                        fb_bp_put_rice(b, fb_zigzag(v3.z), k); fb_bp_put_rice(b, fb_zigzag(v3.w), k);
+                        i += 16;
+                    } else {
+                        fb_bp_put_rice(b, fb_zigzag(data[i]), k);
+                        i++;
+                    }
+                }
+            }
+            fb_bp_finish(b);
+        }
+    }
+    __syncthreads();
 
     /* ---- CRC-16 over the body (crc.c:59-92) ---------------------------------------------
      * The body is cut into T right-aligned chunks of `per` words (virtual zero words in
@@ -425,82 +455,73 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     }
     __syncthreads();
 
-    const uint32_t nbytes = body + 2u;
-    if (in_smem) {
-        const uint32_t nw = (nbytes + 3u) >> 2;
-        for (uint32_t w = tid; w < nw; w += T) gslot[w] = wbuf[w];
+    /* ---- where the frame goes: exclusive prefix of the frame lengths ---------------------
+     * Decoupled look-back (warp 0): walk back over the predecessors' published lengths, 32 at
+     * a time, until one of them already knows its inclusive prefix.  Every predecessor
+     * published its length before it started writing bits, so this rarely has to wait. */
+    if (tid < 32) {
+        const int lane = tid;
+        unsigned long long excl = 0;
+        if (f > 0) {
+            long long base = (long long)f - 1;
+            for (;;) {
+                const long long idx = base - lane;
+                unsigned long long v = FB_SCAN_PREFIX;              /* in front of frame 0: prefix 0 */
+                if (idx >= 0) {
+                    do { v = *(volatile unsigned long long *)&status[idx]; } while ((v >> 62) == 0);
+                }
+                const unsigned pm = __ballot_sync(FB_FULL_MASK, (v >> 62) == 2ull);
+                const int stop = pm ? __ffs((int)pm) - 1 : 31;      /* nearest lane that holds a prefix */
+                excl += fb_warp_sum_u64(lane <= stop ? (v & FB_SCAN_VALUE) : 0ull);
+                if (pm) break;
+                base -= 32;
+            }
+        }
+        if (lane == 0) {
+            if (f > 0) *(volatile unsigned long long *)&status[f] = FB_SCAN_PREFIX | (excl + (unsigned long long)nbytes);
+            s_off = excl;
+        }
+    }
+    __syncthreads();
+    const unsigned long long off = s_off;
+
+    /* ---- staged words (16-byte aligned) -> out + off (any alignment) ---------------------- */
+    {
+        const uint32_t *src = wbuf;
+        uint8_t *dst = out + off;
+        const uint32_t len = nbytes;
+        const uint32_t mis = (uint32_t)((size_t)dst & 3u);
+        const uint32_t head = mis ? min(len, 4u - mis) : 0u;        /* bytes up to the first aligned word */
+        if ((uint32_t)tid < head) dst[tid] = (uint8_t)(src[0] >> (8u * (uint32_t)tid));
+        if (len > head) {
+            uint32_t *dw = (uint32_t *)(dst + head);
+            const uint32_t rest = len - head, nwords = rest >> 2;
+            /* destination word j holds source bytes [head + 4j, head + 4j + 4) */
+            const uint32_t sel = head == 0 ? 0x3210u : head == 1 ? 0x4321u : head == 2 ? 0x5432u : 0x6543u;
+            for (uint32_t j = tid; j < nwords; j += T) {
+                const uint32_t a = src[j], b2 = head ? src[j + 1] : 0u;
+                dw[j] = __byte_perm(a, b2, sel);
+            }
+            const uint32_t tail = rest & 3u;
+            if ((uint32_t)tid < tail) {
+                const uint32_t k = head + nwords * 4u + (uint32_t)tid;
+                dst[k] = (uint8_t)(src[k >> 2] >> (8u * (k & 3u)));
+            }
+        }
     }
     if (tid == 0) {
         frame_len[f] = nbytes;
+        frame_off[f] = off;
         if (frame_bs) frame_bs[f] = (uint32_t)n;
+        atomicMax(&summary->max_frame_bytes, nbytes);
         if (verbatim) {
-            atomicAdd(verbatim_count, 1u);
+            atomicAdd(&summary->verbatim_frames, 1u);
             for (int c = 0; c < C; c++) subs[(size_t)f * C + c].type = 1;
         }
-    }
-}
-
-/* ---------------- compaction ------------------------------------------- */
-/* exclusive scan of frame_len -> frame_off, plus the chunk summary; one CTA */
-__global__ void __launch_bounds__(1024)
-k_offsets(const uint32_t *nframes, const uint32_t *frame_len, uint64_t *frame_off,
-          FbSummary *summary, const uint32_t *verbatim_count)
-{
-    __shared__ uint32_t scan_scratch[33];
-    __shared__ uint64_t red[32];
-    __shared__ unsigned long long carry;
-    const uint32_t nf = *nframes;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    uint32_t mymax = 0;
-    for (uint32_t base = 0; base < nf; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < nf ? frame_len[i] : 0u;
-        mymax = max(mymax, v);
-        uint32_t total;
-        const uint32_t ex = fb_block_exscan_u32(v, scan_scratch, &total);
-        if (i < nf) frame_off[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
-    }
-    mymax = fb_block_max_u32(mymax, red);
-    if (threadIdx.x == 0) {
-        summary->nframes = nf;
-        summary->max_frame_bytes = mymax;
-        summary->total_bytes = carry;
-        summary->verbatim_frames = *verbatim_count;
-        summary->reserved = 0;
-    }
-}
-
-/* one CTA per frame: staged slot (16-byte aligned) -> out + frame_off (any alignment) */
-__global__ void __launch_bounds__(256)
-k_compact(const FbFrame *frames, const uint32_t *nframes, const uint32_t *frame_len,
-          const uint64_t *frame_off, const uint8_t *slots, uint8_t *out)
-{
-    const uint32_t f = blockIdx.x;
-    if (f >= *nframes) return;
-    const uint32_t len = frame_len[f];
-    const uint32_t *src = (const uint32_t *)(slots + frames[f].slot);
-    uint8_t *dst = out + frame_off[f];
-    const uint32_t mis = (uint32_t)((size_t)dst & 3u);
-    /* head bytes up to the first aligned destination word */
-    const uint32_t head = mis ? min(len, 4u - mis) : 0u;
-    if (threadIdx.x < head) dst[threadIdx.x] = ((const uint8_t *)src)[threadIdx.x];
-    if (len <= head) return;
-    uint32_t *dw = (uint32_t *)(dst + head);
-    const uint32_t body = len - head, nwords = body >> 2;
-    /* destination word j holds source bytes [head + 4j, head + 4j + 4) */
-    const uint32_t sel = head == 0 ? 0x3210u : head == 1 ? 0x4321u : head == 2 ? 0x5432u : 0x6543u;
-    for (uint32_t j = threadIdx.x; j < nwords; j += blockDim.x) {
-        const uint32_t a = src[j], b = head ? src[j + 1] : 0u;
-        dw[j] = __byte_perm(a, b, sel);
-    }
-    const uint32_t tail = body & 3u;
-    if (threadIdx.x < tail) {
-        const uint32_t k = head + nwords * 4u + threadIdx.x;
-        dst[k] = ((const uint8_t *)src)[k];
+        if (f == nf - 1) {                                           /* the last frame closes the chunk summary */
+            summary->nframes = nf;
+            summary->total_bytes = off + nbytes;
+        }
     }
 }
 

@@ -120,13 +120,14 @@ FLAKE_API unsigned int flake_b200_subframe_record_size(void);
 
 /*
  * Per-stage device timing of the batch/device engine, measured with CUDA events
- * recorded between the kernels on the launching stream.  Seven stages:
+ * recorded between the kernels on the launching stream.  Five stages:
  * 0 frame table (+VBS split), 1 prepare, 2 LPC analysis, 3 order/Rice search,
- * 4 pack, 5 offsets scan, 6 compaction.  set_profiling(1) clears the totals;
- * stage_times() synchronises the recorded events and returns cumulative
- * milliseconds and pass counts per stage (arrays of 7).
+ * 4 pack (bits, CRCs, frame offsets, frames written back to back).
+ * set_profiling(1) clears the totals; stage_times() synchronises the recorded
+ * events and returns cumulative milliseconds and pass counts per stage (arrays of
+ * FLAKE_B200_NUM_STAGES).
  */
-#define FLAKE_B200_NUM_STAGES 7
+#define FLAKE_B200_NUM_STAGES 5
 FLAKE_API int flake_b200_set_profiling(FlakeContext *s, int on);
 FLAKE_API int flake_b200_stage_times(FlakeContext *s, double *ms, unsigned long long *launches);
 

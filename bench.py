@@ -390,8 +390,11 @@ def run_gpu_arm(args):
     multi = None
     nstreams = env_int("FLAKE_BENCH_STREAMS", max(1, min(8, (os.cpu_count() or 2) // (2 * max(1, world)))))
     if nstreams > 1 and not os.environ.get("FLAKE_BENCH_SKIP_MULTI"):
+        # no collective inside the try: a rank that fails must still reach the reductions below
+        best, same, why = float("nan"), False, None
+        encs = []
         try:
-            encs, outs, flens = [], [], []
+            outs, flens = [], []
             for _ in range(nstreams):
                 e = api.Encoder(lib, CHANNELS, RATE, BPS, nsamples, LEVEL)
                 e.init()
@@ -408,10 +411,9 @@ def run_gpu_arm(args):
                                                       nblocks + 1, C.byref(n_out))
                 encs[i].streaminfo()
 
-            best = None
             for it in range(2):
                 ths = [threading.Thread(target=one, args=(i,)) for i in range(nstreams)]
-                barrier()
+                torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 for th in ths:
                     th.start()
@@ -422,20 +424,25 @@ def run_gpu_arm(args):
                     raise RuntimeError("flake_b200_encode_stream failed: %s" % rcs)
                 if it >= 1:
                     best = dt
-            same = all(bytes(outs[i][:int(rcs[i])].numpy().tobytes()) == bytes(outs[0][:int(rcs[0])].numpy().tobytes())
-                       for i in range(1, min(nstreams, 2)))
-            t = torch.tensor([best], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            same = bytes(outs[1][:int(rcs[1])].numpy().tobytes()) == bytes(outs[0][:int(rcs[0])].numpy().tobytes())
+            del outs
+        except Exception as exc:            # informative only
+            why = str(exc)[:200]
+        for e in encs:
+            try:
+                e.close()
+            except Exception:
+                pass
+        t = torch.tensor([best if best == best else 1e30], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if float(t.item()) < 1e29:
             multi = {"value": round(world * nstreams * nsamples / float(t.item()) / 1e6, 2), "unit": "MSamples/s",
                      "streams_per_gpu": nstreams, "ms": round(float(t.item()) * 1e3, 1), "outputs_identical": bool(same),
                      "note": "independent 1 h streams encoded concurrently through the host-buffer C ABI, "
-                             "one context + MD5 thread each (the C5 corpus shape)"}
-            for e in encs:
-                e.close()
-            del outs
-        except Exception as exc:            # informative only
-            multi = {"value": None, "error": str(exc)[:200]}
+                             "one context + MD5 thread each (the C5 corpus shape); ranks not barrier-aligned"}
+        else:
+            multi = {"value": None, "error": why or "failed on another rank"}
 
     if rank != 0:
         enc.close()

@@ -376,6 +376,7 @@ extern "C" int fb_cuda_sm_count(int device)
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return 0;
     return cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) == cudaSuccess ? n : 0;
 }
+extern "C" int fb_cuda_current_device(void) { int d = -1; return cudaGetDevice(&d) == cudaSuccess ? d : -1; }
 extern "C" int fb_cuda_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -1; }
 
 #ifdef FLAKE_B200_CUDA_EMU

@@ -128,6 +128,7 @@ int   fb_cuda_stream_wait_event(void *stream, void *ev);
 float fb_cuda_event_elapsed_ms(void *a, void *b);
 int   fb_cuda_device_count(void);
 int   fb_cuda_sm_count(int device);            /* < 0: current device */
+int   fb_cuda_current_device(void);           /* -1 on error */
 int   fb_cuda_set_device(int dev);
 
 #ifdef __cplusplus

@@ -26,7 +26,8 @@
 
 #define FB_VERSION "SVN"
 #define FB_FALLBACK_CHUNK_BLOCKS 2048
-#define FB_CHUNK_TARGET_INTS (80u << 20)      /* channel-samples per chunk the default aims for */
+#define FB_CHUNK_DEVICE_INTS (320u << 20)     /* channel-samples per pass: device-resident API, stream length known */
+#define FB_CHUNK_HOST_INTS (80u << 20)        /* host streaming path (pipelined lanes), or length unknown */
 
 typedef struct FbLane {
     void *h_in, *d_in;              /* pinned staging + device copy of the chunk's PCM */
@@ -55,8 +56,10 @@ typedef struct FbCtx {
     size_t frame_buffer_size;
     FbLane one;
     /* batch path */
-    FbEngine *engN;
-    int chunk_blocks;
+    FbEngine *engN;             /* host streaming path: chunk_blocks per pass, two lanes */
+    FbEngine *engD;             /* device-resident API: dev_chunk_blocks per pass */
+    FbEngine *last_engine;      /* whichever ran the most recent pass */
+    int chunk_blocks, dev_chunk_blocks;
     FbLane lane[2];
     int lanes_ready;
     void *st, *st_copy, *ev_a, *ev_b;
@@ -66,7 +69,7 @@ typedef struct FbCtx {
 
 static int g_device = -2;           /* -2: not chosen yet */
 struct FbCtx;
-static int default_chunk_blocks(const struct FbCtx *c, unsigned int stream_samples);
+static int default_chunk_blocks(const struct FbCtx *c, unsigned int stream_samples, uint64_t target_ints);
 
 static double now_ms(void)
 {
@@ -413,6 +416,7 @@ static int lane_launch(FbCtx *c, FbEngine *e, FbLane *l, const void *upload, siz
                                            l->d_flen, l->d_fbs, l->d_sum, c->st);
     if (rc) { snprintf(c->err, sizeof c->err, "%s", fb_engine_last_error(e)); return -3; }
     c->stats.kernel_launches += fb_engine_launch_count(e) - before;
+    c->last_engine = e;
     if (fb_cuda_d2h(l->h_sum, l->d_sum, sizeof(FbSummary), c->st)) return -3;
     c->stats.d2h_bytes += sizeof(FbSummary);
     if (fb_cuda_event_record(l->ev_done, c->st)) return -3;
@@ -452,10 +456,18 @@ static void ctx_free(FbCtx *c)
     lane_free(&c->lane[0]); lane_free(&c->lane[1]);
     if (c->eng1) fb_engine_destroy(c->eng1);
     if (c->engN) fb_engine_destroy(c->engN);
+    if (c->engD) fb_engine_destroy(c->engD);
     fb_cuda_free_host(c->frame_buffer);
     fb_cuda_event_destroy(c->ev_a); fb_cuda_event_destroy(c->ev_b);
     fb_cuda_stream_destroy(c->st); fb_cuda_stream_destroy(c->st_copy);
     free(c);
+}
+
+/* The CUDA current device is per host thread: every entry point that touches the device binds
+ * the calling thread to the context's device first (callers may use one thread per stream). */
+static void ctx_bind_device(const FbCtx *c)
+{
+    if (c->device >= 0) fb_cuda_set_device(c->device);
 }
 
 int flake_b200_set_device(int device)
@@ -524,8 +536,9 @@ int flake_encode_init(FlakeContext *s)
         const char *env = getenv("FLAKE_B200_DEVICE");
         g_device = env ? atoi(env) : -1;
     }
-    c->device = g_device;
-    c->chunk_blocks = default_chunk_blocks(c, s->samples);
+    c->device = g_device >= 0 ? g_device : fb_cuda_current_device();
+    c->chunk_blocks = default_chunk_blocks(c, s->samples, FB_CHUNK_HOST_INTS);
+    c->dev_chunk_blocks = default_chunk_blocks(c, s->samples, s->samples ? FB_CHUNK_DEVICE_INTS : FB_CHUNK_HOST_INTS);
     c->eng1 = fb_engine_create(g, c->device, 1, c->err, sizeof c->err);
     if (!c->eng1) {
         fprintf(stderr, "flake_b200: cannot create the CUDA engine: %s\n", c->err);
@@ -563,6 +576,7 @@ void *flake_get_buffer(const FlakeContext *s)
 void flake_encode_close(FlakeContext *s)
 {
     if (!s || !s->private_ctx) return;
+    ctx_bind_device((FbCtx *)s->private_ctx);
     ctx_free((FbCtx *)s->private_ctx);
     free(s->header);
     s->header = NULL;
@@ -592,6 +606,7 @@ int flake_encode_frame(FlakeContext *s, const int *samples, int block_size)
     if (block_size < 1 || block_size > c->params.block_size) return -1;
     if (c->last_frame) return -1;
     if (!c->params.allow_vbs && block_size != c->params.block_size) c->last_frame = 1;
+    ctx_bind_device(c);
 
     if (lane_submit(c, c->eng1, &c->one, samples, FLAKE_B200_PCM_S32, (uint64_t)block_size, c->frame_count))
         return -1;
@@ -653,18 +668,23 @@ static void *md5_worker(void *arg)
 
 /*
  * Blocks per engine pass.  Every kernel's grid is a multiple of the block count, so the
- * default is a multiple of the device's SM count (B200: 148 x 64 = 9472 blocks of 4096 stereo
- * samples, about 80 M channel-samples): whole waves for the per-subframe grids and two lane
- * pairs' worth of warps per scheduler for k_lpc.  Streams shorter than that get an engine of
- * their own size.  FLAKE_B200_CHUNK_BLOCKS overrides.
+ * defaults are multiples of the device's SM count (whole waves for the per-subframe grids).
+ *   device-resident API: up to 320 Mi channel-samples (B200: 148 x 276 = 40,848 blocks of 4096
+ *     stereo samples, 1.25 GB per int32 plane buffer).  k_lpc is a lane pair per subframe,
+ *     i.e. only subframes/16 warps: 8 warps per scheduler instead of 2 (measured on a 1-hour
+ *     stream: 7.59 ms per pass with 10,212-block chunks, 7.16 ms in one pass);
+ *   host streaming path: 80 Mi, so that upload, kernels, download and MD5 of different chunks
+ *     overlap and the pinned lanes stay small; also when the stream length is not known.
+ * Streams shorter than that get an engine of their own size.  FLAKE_B200_CHUNK_BLOCKS and
+ * flake_b200_set_chunk_blocks() override both.
  */
-static int default_chunk_blocks(const FbCtx *c, unsigned int stream_samples)
+static int default_chunk_blocks(const FbCtx *c, unsigned int stream_samples, uint64_t target_ints)
 {
     const char *cb = getenv("FLAKE_B200_CHUNK_BLOCKS");
     if (cb && atoi(cb) >= 1) return atoi(cb);
     const uint64_t per_block = (uint64_t)c->params.block_size * (uint64_t)c->channels;
     const int sms = fb_cuda_sm_count(c->device);
-    uint64_t blocks = FB_CHUNK_TARGET_INTS / (per_block ? per_block : 1);
+    uint64_t blocks = target_ints / (per_block ? per_block : 1);
     if (sms > 0 && blocks >= (uint64_t)sms) blocks -= blocks % (uint64_t)sms;
     if (blocks < 1) blocks = 1;
     if (sms <= 0 && blocks > FB_FALLBACK_CHUNK_BLOCKS) blocks = FB_FALLBACK_CHUNK_BLOCKS;
@@ -679,12 +699,20 @@ int flake_b200_set_chunk_blocks(FlakeContext *s, int blocks)
 {
     if (!s || !s->private_ctx || blocks < 1) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
+    ctx_bind_device(c);
     if (c->engN && blocks != c->chunk_blocks) {
         fb_cuda_stream_sync(c->st);
         lane_free(&c->lane[0]); lane_free(&c->lane[1]);
+        if (c->last_engine == c->engN) c->last_engine = NULL;
         fb_engine_destroy(c->engN); c->engN = NULL; c->lanes_ready = 0;
     }
+    if (c->engD && blocks != c->dev_chunk_blocks) {
+        fb_cuda_stream_sync(c->st);
+        if (c->last_engine == c->engD) c->last_engine = NULL;
+        fb_engine_destroy(c->engD); c->engD = NULL;
+    }
     c->chunk_blocks = blocks;
+    c->dev_chunk_blocks = blocks;
     return 0;
 }
 
@@ -721,6 +749,7 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
 {
     if (!s || !s->private_ctx || !pcm || !out) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
+    ctx_bind_device(c);
     if (fmt < FLAKE_B200_PCM_S32 || fmt > FLAKE_B200_PCM_S8) return -1;
     if (nframes_out) *nframes_out = 0;
     if (nsamples == 0) return 0;
@@ -890,13 +919,14 @@ int flake_b200_device_capacity(FlakeContext *s, unsigned long long *max_samples,
 {
     if (!s || !s->private_ctx) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    if (!c->engN) {
-        c->engN = fb_engine_create(&c->cfg, c->device, (uint32_t)c->chunk_blocks, c->err, sizeof c->err);
-        if (!c->engN) return -3;
+    ctx_bind_device(c);
+    if (!c->engD) {
+        c->engD = fb_engine_create(&c->cfg, c->device, (uint32_t)c->dev_chunk_blocks, c->err, sizeof c->err);
+        if (!c->engD) return -3;
     }
-    if (max_samples) *max_samples = (unsigned long long)fb_engine_max_blocks(c->engN) * (unsigned long long)c->params.block_size;
-    if (out_bytes) *out_bytes = fb_engine_out_capacity(c->engN);
-    if (max_frames) *max_frames = fb_engine_max_frames(c->engN);
+    if (max_samples) *max_samples = (unsigned long long)fb_engine_max_blocks(c->engD) * (unsigned long long)c->params.block_size;
+    if (out_bytes) *out_bytes = fb_engine_out_capacity(c->engD);
+    if (max_frames) *max_frames = fb_engine_max_frames(c->engD);
     return 0;
 }
 
@@ -907,12 +937,13 @@ int flake_b200_encode_device(FlakeContext *s, const void *d_pcm, int fmt, unsign
     if (!s || !s->private_ctx || !d_pcm || !d_out || !d_summary) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
     if (flake_b200_device_capacity(s, NULL, NULL, NULL)) return -3;
-    const uint64_t before = fb_engine_launch_count(c->engN);
-    const int rc = fb_engine_encode_device(c->engN, d_pcm, fmt, nsamples, first_number, d_out,
+    const uint64_t before = fb_engine_launch_count(c->engD);
+    const int rc = fb_engine_encode_device(c->engD, d_pcm, fmt, nsamples, first_number, d_out,
                                            d_frame_len, d_frame_bs, (FbSummary *)d_summary,
                                            cuda_stream ? cuda_stream : c->st);
-    c->stats.kernel_launches += fb_engine_launch_count(c->engN) - before;
-    if (rc) snprintf(c->err, sizeof c->err, "%s", fb_engine_last_error(c->engN));
+    c->stats.kernel_launches += fb_engine_launch_count(c->engD) - before;
+    c->last_engine = c->engD;
+    if (rc) snprintf(c->err, sizeof c->err, "%s", fb_engine_last_error(c->engD));
     return rc;
 }
 
@@ -921,17 +952,17 @@ int flake_b200_set_profiling(FlakeContext *s, int on)
     if (!s || !s->private_ctx) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
     if (flake_b200_device_capacity(s, NULL, NULL, NULL)) return -3;
-    if (on) fb_engine_reset_timing(c->engN);
-    return fb_engine_set_timing(c->engN, on);
+    if (on) fb_engine_reset_timing(c->engD);
+    return fb_engine_set_timing(c->engD, on);
 }
 
 int flake_b200_stage_times(FlakeContext *s, double *ms, unsigned long long *launches)
 {
     if (!s || !s->private_ctx) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    if (!c->engN) return -1;
+    if (!c->engD) return -1;
     uint64_t l[FB_NUM_STAGES];
-    const int n = fb_engine_collect_timing(c->engN, ms, l);
+    const int n = fb_engine_collect_timing(c->engD, ms, l);
     if (launches) for (int i = 0; i < FB_NUM_STAGES; i++) launches[i] = l[i];
     return n;
 }
@@ -942,7 +973,8 @@ int flake_b200_last_subframes(FlakeContext *s, void *subs, unsigned int max)
 {
     if (!s || !s->private_ctx || !subs) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    FbEngine *e = c->engN ? c->engN : c->eng1;
+    ctx_bind_device(c);
+    FbEngine *e = c->last_engine ? c->last_engine : c->eng1;
     return fb_engine_read_subframes(e, (FbSub *)subs, max, c->st);
 }
 

@@ -4,6 +4,7 @@ oracle restatement (and the compiled reference when oracle/_ref travelled with t
 Bar: bit-exact frames, header and final STREAMINFO; the stream must also decode
 back to the input with all CRCs and the MD5 valid.
 """
+import ctypes as C
 import zlib
 
 import numpy as np
@@ -145,3 +146,29 @@ def test_int32_input_beyond_24_bits_estimate_is_exact(gpu_lib, oracle):
     got = api.encode_batch(gpu_lib, pcm, 44100, 16, 8, chunk_blocks=2)
     want, flen, fbs, mx = oracle.encode_stream(pcm, 44100, 16, 8)
     assert got.payload == want
+
+
+def test_encode_stream_from_worker_threads(gpu_lib, oracle):
+    """The CUDA current device is per host thread; a context must work from any thread (bench.py
+    encodes several streams concurrently, one thread each)."""
+    import threading
+    pcm = synth.synth_pcm(4096 * 6 + 100, 2, 16, 44100, seed=21)
+    want, flen, fbs, mx = oracle.encode_stream(pcm, 44100, 16, 8)
+    encs = [api.Encoder(gpu_lib, 2, 44100, 16, pcm.shape[0], 8) for _ in range(3)]
+    for e in encs:
+        e.init()
+    got = [None] * 3
+
+    def work(i):
+        for _ in range(2):                      # second round: engine and lanes already exist
+            gpu_lib.flake_b200_reset_stream(C.byref(encs[i].ctx))
+            got[i] = encs[i].encode_stream(pcm, api.PCM_S32, pcm.shape[0])
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for e in encs:
+        e.close()
+    assert all(g is not None and g[0].tobytes() == want for g in got)

@@ -758,21 +758,22 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         while (step > 0) {
             int cnt = 0, idx[FB_GROUP], nsteps = 0;
             uint32_t gmask = 0, hyp = 1u << opt_order;
+            const int lane = tid & 31;
+            const uint32_t range = (hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
             for (int s = step; s > 0; s >>= 1) {
-                uint32_t cfirst = 0;
-                bool same = true, first = true;
-                for (uint32_t hm = hyp; hm; hm &= hm - 1) {
-                    const int h = __ffs((int)hm) - 1;
-                    uint32_t cm = 0;
-                    for (int i = h - s; i <= h + s; i += s)
-                        if (i >= lo && i <= hi) cm |= 1u << i;
-                    cm &= ~(done | gmask);
-                    if (first) { cfirst = cm; first = false; }
-                    else if (cm != cfirst) same = false;
-                }
-                if (!same || cnt + __popc(cfirst) > FB_GROUP) break;
-                for (uint32_t m = cfirst; m; m &= m - 1) { idx[cnt] = __ffs((int)m) - 1; ord[cnt] = idx[cnt] + 1; cnt++; }
-                gmask |= cfirst; hyp |= cfirst; nsteps++;
+                /* lane h plays hypothesis `last == h`: its candidates {h-s, h, h+s} inside the
+                 * order range and not yet costed; the step joins the group when all live
+                 * hypotheses agree (OR == AND over them) */
+                const bool live = (hyp >> lane) & 1u;
+                uint32_t cm = 1u << lane;
+                if (lane - s >= 0) cm |= 1u << (lane - s);
+                if (lane + s < 32) cm |= 1u << (lane + s);
+                cm &= range & ~(done | gmask);
+                const uint32_t cor = __reduce_or_sync(FB_FULL_MASK, live ? cm : 0u);
+                const uint32_t cand = __reduce_and_sync(FB_FULL_MASK, live ? cm : 0xffffffffu);
+                if (cor != cand || cnt + __popc(cor) > FB_GROUP) break;
+                for (uint32_t m = cor; m; m &= m - 1) { idx[cnt] = __ffs((int)m) - 1; ord[cnt] = idx[cnt] + 1; cnt++; }
+                gmask |= cor; hyp |= cor; nsteps++;
             }
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
             for (int k = 0; k < nsteps; k++, step >>= 1) {

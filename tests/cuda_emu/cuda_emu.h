@@ -190,6 +190,16 @@ inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
     cuemu::warp_barrier(mask);
     return r;
 }
+inline unsigned __reduce_and_sync(unsigned mask, unsigned v)
+{
+    cuemu::WarpState &w = cuemu::my_warp();
+    w.slot[cuemu::lane_id()] = v;
+    cuemu::warp_barrier(mask);
+    unsigned r = 0xffffffffu;
+    for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r &= (unsigned)w.slot[l];
+    cuemu::warp_barrier(mask);
+    return r;
+}
 inline unsigned __reduce_max_sync(unsigned mask, unsigned v)
 {
     cuemu::WarpState &w = cuemu::my_warp();

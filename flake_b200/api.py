@@ -111,6 +111,8 @@ def load_library(path: Optional[str] = None, extension: bool = True) -> C.CDLL:
         lib.flake_b200_set_profiling.argtypes = [P(FlakeContext), C.c_int]; lib.flake_b200_set_profiling.restype = C.c_int
         lib.flake_b200_stage_times.argtypes = [P(FlakeContext), P(C.c_double), P(C.c_ulonglong)]
         lib.flake_b200_stage_times.restype = C.c_int
+        lib.flake_b200_write_seektable.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_ulonglong]
+        lib.flake_b200_write_seektable.restype = C.c_longlong
         lib.flake_b200_get_stats.argtypes = [P(FlakeContext), P(FlakeB200Stats)]; lib.flake_b200_get_stats.restype = C.c_int
         lib.flake_b200_last_error.argtypes = [P(FlakeContext)]; lib.flake_b200_last_error.restype = C.c_char_p
         lib.flake_b200_version.argtypes = []; lib.flake_b200_version.restype = C.c_char_p

@@ -985,6 +985,35 @@ int flake_b200_get_stats(const FlakeContext *s, FlakeB200Stats *st)
     return 0;
 }
 
+long long flake_b200_write_seektable(const unsigned int *frame_len, const unsigned int *frame_bs,
+                                     unsigned int nframes, unsigned int interval_samples,
+                                     unsigned char *data, unsigned long long cap)
+{
+    if (!frame_len || !frame_bs) return -1;
+    unsigned long long sample = 0, offset = 0, next = 0, written = 0;
+    for (unsigned int f = 0; f < nframes; f++) {
+        if (sample >= next) {
+            if (data) {
+                if (written + 18u > cap) return -1;
+                unsigned char *p = data + written;
+                for (int i = 0; i < 8; i++) p[i] = (unsigned char)(sample >> (56 - 8 * i));
+                for (int i = 0; i < 8; i++) p[8 + i] = (unsigned char)(offset >> (56 - 8 * i));
+                p[16] = (unsigned char)(frame_bs[f] >> 8);
+                p[17] = (unsigned char)frame_bs[f];
+            }
+            written += 18u;
+            if (interval_samples) {
+                while (next <= sample) next += interval_samples;
+            } else {
+                next = sample + 1;
+            }
+        }
+        sample += frame_bs[f];
+        offset += frame_len[f];
+    }
+    return (long long)written;
+}
+
 const char *flake_b200_last_error(const FlakeContext *s)
 {
     if (!s || !s->private_ctx) return "no context";

@@ -131,6 +131,20 @@ FLAKE_API unsigned int flake_b200_subframe_record_size(void);
 FLAKE_API int flake_b200_set_profiling(FlakeContext *s, int on);
 FLAKE_API int flake_b200_stage_times(FlakeContext *s, double *ms, unsigned long long *launches);
 
+/*
+ * SEEKTABLE from the per-frame lengths and block sizes that the batch calls return
+ * (the reference writes none, so this is opt-in and not part of the
+ * byte-identical stream).  One seek point for the first frame that starts at or after every
+ * multiple of `interval_samples` (0: one per frame).  Each point is the FLAC triple
+ * {sample number of the frame's first sample (u64 BE), byte offset from the first frame
+ * (u64 BE), samples in the frame (u16 BE)} = 18 bytes; `data` receives the metadata block
+ * BODY (the caller adds the 4-byte block header, type 3).  Returns the number of bytes
+ * written, the number needed when data == NULL, or -1 when `cap` is too small.
+ */
+FLAKE_API long long flake_b200_write_seektable(const unsigned int *frame_len, const unsigned int *frame_bs,
+                                               unsigned int nframes, unsigned int interval_samples,
+                                               unsigned char *data, unsigned long long cap);
+
 FLAKE_API int flake_b200_get_stats(const FlakeContext *s, FlakeB200Stats *stats);
 FLAKE_API const char *flake_b200_last_error(const FlakeContext *s);
 FLAKE_API const char *flake_b200_version(void);

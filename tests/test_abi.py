@@ -138,3 +138,34 @@ def test_product_does_not_link_the_oracle():
     assert "orc_" not in out
     out = subprocess.run(["ldd", api.DEFAULT_LIB], capture_output=True, text=True).stdout
     assert "oracle" not in out and "emu" not in out
+
+
+def test_seektable_from_frame_lengths(lib):
+    """flake_b200_write_seektable: FLAC seek points (sample u64, offset u64, samples u16, big endian)
+    from the per-frame lengths / block sizes of a batch call; host-only code."""
+    import numpy as np
+    import struct
+    flen = np.array([100, 250, 90, 300, 120, 80, 70], dtype=np.uint32)
+    fbs = np.array([4096, 4096, 2048, 2048, 4096, 4096, 1000], dtype=np.uint32)
+
+    def expect(interval):
+        pts, sample, off, nxt = [], 0, 0, 0
+        for l, b in zip(flen, fbs):
+            if sample >= nxt:
+                pts.append(struct.pack(">QQH", sample, off, int(b)))
+                if interval:
+                    while nxt <= sample:
+                        nxt += interval
+                else:
+                    nxt = sample + 1
+            sample += int(b); off += int(l)
+        return b"".join(pts)
+
+    for interval in (0, 4096, 6000, 10000, 1 << 30):
+        need = lib.flake_b200_write_seektable(flen.ctypes.data, fbs.ctypes.data, len(flen), interval, None, 0)
+        want = expect(interval)
+        assert need == len(want)
+        buf = (C.c_ubyte * need)()
+        got = lib.flake_b200_write_seektable(flen.ctypes.data, fbs.ctypes.data, len(flen), interval, buf, need)
+        assert got == need and bytes(buf) == want
+        assert lib.flake_b200_write_seektable(flen.ctypes.data, fbs.ctypes.data, len(flen), interval, buf, need - 1) == -1

@@ -116,6 +116,29 @@ __device__ __forceinline__ uint32_t fb_block_exscan_u32(uint32_t v, uint32_t *sc
     return base + inc - v;
 }
 
+/* Same, with ONE barrier: `scratch` must not be written again before another barrier has
+ * been passed by the whole CTA (callers give every scan its own scratch row). */
+__device__ __forceinline__ uint32_t fb_block_exscan_u32_once(uint32_t v, uint32_t *scratch, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FB_FULL_MASK, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, all = 0;
+    for (int w = 0; w < nw; w++) {
+        uint32_t s = scratch[w];
+        if (w < warp) base += s;
+        all += s;
+    }
+    *total = all;
+    return base + inc - v;
+}
+
 /* ------------------------------------------------------------------ */
 /* integer helpers with the reference's exact semantics                 */
 /* ------------------------------------------------------------------ */

@@ -180,6 +180,7 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     __shared__ uint32_t s_ticket;
     __shared__ unsigned long long s_off;
     __shared__ uint32_t scan_scratch[33];
+    __shared__ uint32_t ch_scratch[FB_MAX_CH_UNROLL][32];   /* one scan row per subframe: one barrier per scan */
     __shared__ __align__(16) uint16_t crc_tab[4][256];
     __shared__ uint32_t s_hdr_len;
     __shared__ uint8_t s_hdr[24];
@@ -256,7 +257,15 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
     uint64_t chbit[FB_MAX_CH_UNROLL];                /* first bit of each subframe */
     uint64_t total_bits = 0;
     bool verbatim = false;
+    /* Rice parameters of every subframe into shared memory */
+    for (int c = 0; c < C; c++) {
+        const FbSub *sb = &subs[(size_t)f * C + c];
+        if (sb->type == 8 || sb->type == 32)
+            for (int j = tid; j < (1 << sb->porder); j += T) s_params[c][j] = sb->params[j];
+    }
+    __syncthreads();
     for (int pass = 0; pass < 2; pass++) {
+        if (pass) __syncthreads();                   /* the scan rows of the first round are free again */
         uint64_t bitpos = (uint64_t)hdr_len * 8u;
         for (int c = 0; c < C; c++) {
             const FbSub *sb = &subs[(size_t)f * C + c];
@@ -264,13 +273,8 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
             const size_t off = (size_t)fr.start * C + (size_t)c * n;
             const int32_t *data = (L.type == 1 || L.type == 0) ? smp + off : res + off;
             const bool rice = (L.type == 8 || L.type == 32);
-            uint8_t *kp = s_params[c];
+            const uint8_t *kp = s_params[c];
 
-            /* Rice parameters of this subframe into shared memory */
-            if (rice) {
-                for (int j = tid; j < (1 << L.porder); j += T) kp[j] = sb->params[j];
-                __syncthreads();
-            }
             /* The partition index is tracked incrementally; 16 samples that lie in one
              * partition and start 16-byte aligned are taken with four 128-bit loads and one
              * Rice parameter */
@@ -302,7 +306,7 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
                 }
             }
             uint32_t sub_tokens;
-            myoff[c] = fb_block_exscan_u32(mybits, scan_scratch, &sub_tokens);
+            myoff[c] = fb_block_exscan_u32_once(mybits, ch_scratch[c], &sub_tokens);
             chbit[c] = bitpos;
             bitpos += (uint64_t)L.preamble_bits + sub_tokens;
         }

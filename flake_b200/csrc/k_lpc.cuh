@@ -51,15 +51,27 @@ template <int ML> struct FbLpcGeom {
     static constexpr int LD = (TL + 31) / 32;            /* 32-lane loads per staged row */
 };
 
-/* data1[p] of lpc.c:46-56 for a sample value xv at position p (xv == 0 for p >= n).  The
- * window depends only on min(p, n-1-p) (lpc.c:33-39).  Odd n: the centre sample is
- * uninitialised in the reference; defined as 0.0 here (parity-exempt). */
+/* w_i of lpc.c:33-39 for i = min(p, n-1-p) */
+__device__ __forceinline__ double fb_welch(int i, double cc)
+{
+    const double d = __dsub_rn(cc, (double)i);
+    return __dsub_rn(1.0, __dmul_rn(d, d));
+}
+
+/* data1[p] of lpc.c:46-56 for a sample value xv at position p.  The caller passes xv == 0
+ * for p >= n and for the centre of an odd block (uninitialised in the reference, defined as
+ * zero here, parity-exempt), which makes the product +-0.0: adding it never changes a sum
+ * that started at 1.0.  (A per-block-size table of the window was measured: the loads cost
+ * more than the three FP64 operations they save, 0.92 vs 0.85 ms per C2 stream.) */
 __device__ __forceinline__ double fb_windowed(int32_t xv, int p, int n, double cc)
 {
-    const int i = min(p, n - 1 - p);
-    const double d = __dsub_rn(cc, (double)i);
-    const double v = __dmul_rn((double)xv, __dsub_rn(1.0, __dmul_rn(d, d)));
-    return ((n & 1) && p == (n >> 1)) ? 0.0 : v;
+    return __dmul_rn((double)xv, fb_welch(min(p, n - 1 - p), cc));
+}
+
+/* the sample the analysis sees at position p of a plane of n samples */
+__device__ __forceinline__ int32_t fb_lpc_sample(const int32_t *x, int p, int n)
+{
+    return (p >= 0 && p < n && !((n & 1) && p == (n >> 1))) ? x[p] : 0;
 }
 
 /* lpc.c:167-219 with precision 15 (encode.c:443).  `in` is modified like the reference's
@@ -141,6 +153,7 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
     __shared__ int32_t s_rows[FB_LPC_WARPS][2][16 * FB_LPC_ROW];
     __shared__ const int32_t *s_ptr[FB_LPC_WARPS][16];
     __shared__ int s_n[FB_LPC_WARPS][16];
+    __shared__ int s_hole[FB_LPC_WARPS][16];          /* centre of an odd block, else -1 */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ca = lane & 1, row = lane >> 1;
@@ -164,7 +177,7 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
     }
     const int nmax = (int)__reduce_max_sync(FB_FULL_MASK, (unsigned)n);
     if (nmax == 0) return;                               /* warp-uniform */
-    if (ca == 0) { s_ptr[warp][row] = x; s_n[warp][row] = n; }
+    if (ca == 0) { s_ptr[warp][row] = x; s_n[warp][row] = n; s_hole[warp][row] = (n & 1) ? (n >> 1) : -1; }
     __syncwarp();
 
     const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
@@ -174,7 +187,7 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
     {
         double d0[ML + 1];
 #pragma unroll
-        for (int p = 0; p <= ML; p++) d0[p] = fb_windowed(p < n ? x[p] : 0, p, n, cc);
+        for (int p = 0; p <= ML; p++) d0[p] = fb_windowed(fb_lpc_sample(x, p, n), p, n, cc);
 #pragma unroll
         for (int i = 0; i <= ML; i++) {
             double s = 1.0;
@@ -193,9 +206,9 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
 #pragma unroll
     for (int k = 0; k < G::K; k++) {
         const int p = lag - 1 - k + ca;
-        D[k] = fb_windowed((p >= 0 && p < n) ? x[p] : 0, p, n, cc);
+        D[k] = fb_windowed(fb_lpc_sample(x, p, n), p, n, cc);
     }
-    double other_prev = fb_windowed(lag < n ? x[lag] : 0, lag, n, cc);
+    double other_prev = fb_windowed(fb_lpc_sample(x, lag, n), lag, n, cc);
 
     const int P0 = lag + 1;
     const int ntiles = (nmax - P0 + G::TL - 1) / G::TL;
@@ -207,11 +220,11 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
         _Pragma("unroll")                                                                 \
         for (int r = 0; r < 16; r++) {                                                    \
             const int32_t *rp = s_ptr[warp][r];                                           \
-            const int rn = s_n[warp][r];                                                  \
+            const int rn = s_n[warp][r], rh = s_hole[warp][r];                            \
             _Pragma("unroll")                                                             \
             for (int l = 0; l < G::LD; l++) {                                             \
                 const int p = (tb) + lane + 32 * l;                                       \
-                pre[r * G::LD + l] = (lane + 32 * l < G::TL && p < rn) ? rp[p] : 0;       \
+                pre[r * G::LD + l] = (lane + 32 * l < G::TL && p < rn && p != rh) ? rp[p] : 0; \
             }                                                                             \
         }                                                                                 \
     } while (0)

@@ -19,10 +19,7 @@
 
 #include "dev_common.cuh"
 
-#define FB_PACK_THREADS 256
-#ifndef FB_PACK_MINBLOCKS
-#define FB_PACK_MINBLOCKS 1
-#endif
+#define FB_PACK_THREADS 256      /* 59 registers: four CTAs per SM; register caps for 5, 6, 8 measured slower (spills) */
 
 /* ---------------- CRC helpers ---------------------------------------- */
 __device__ __forceinline__ uint32_t fb_crc16_byte(uint32_t crc, uint32_t byte)
@@ -172,7 +169,7 @@ __device__ __forceinline__ FbSubLayout fb_sub_layout(const FbSub *sb, int n, boo
  * ticket / status: zeroed before the launch.  Frames are taken in ticket order (not blockIdx
  * order), so every frame a CTA looks back at belongs to a CTA that is already running or done.
  */
-__global__ void __launch_bounds__(FB_PACK_THREADS, FB_PACK_MINBLOCKS)
+__global__ void __launch_bounds__(FB_PACK_THREADS)
 k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
        const int32_t *res, FbSub *subs, const uint8_t *ch_modes, uint8_t *slots,
        uint32_t *frame_len, uint32_t *frame_bs, int smem_words,

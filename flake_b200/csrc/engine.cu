@@ -379,6 +379,15 @@ extern "C" int fb_cuda_sm_count(int device)
 extern "C" int fb_cuda_current_device(void) { int d = -1; return cudaGetDevice(&d) == cudaSuccess ? d : -1; }
 extern "C" int fb_cuda_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : -1; }
 
+#ifdef FB_SEARCH_PROF
+extern "C" __attribute__((visibility("default"))) int flake_b200_debug_search_prof(unsigned long long *out, int reset)
+{
+    if (out && cudaMemcpyFromSymbol(out, g_sprof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_sprof, z, sizeof z); }
+    return 0;
+}
+#endif
+
 #ifdef FLAKE_B200_CUDA_EMU
 /* hooks for the host-side unit tests of device helpers (emulated build only) */
 extern "C" int fb_test_rice_k(uint64_t sum, int n) { return fb_rice_k(sum, n); }

@@ -36,6 +36,20 @@
 
 #define FB_GROUP 3                  /* candidates evaluated between two decisions */
 
+/* dev builds (-DFB_SEARCH_PROF): cycles per phase as seen by thread 0, summed over all CTAs */
+#ifdef FB_SEARCH_PROF
+__device__ unsigned long long g_sprof[16];
+#define FB_PROF_DECL long long prof_t = clock64()
+#define FB_PROF(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_sprof[(i)], (unsigned long long)(now_ - prof_t)); prof_t = now_; } } while (0)
+#define FB_PROF_ARG , long long &prof_t
+#define FB_PROF_PASS , prof_t
+#else
+#define FB_PROF_DECL do { } while (0)
+#define FB_PROF(i) do { } while (0)
+#define FB_PROF_ARG
+#define FB_PROF_PASS
+#endif
+
 template <int MAXP>
 struct FbSearchShared {
     unsigned long long sums[256];   /* finest-level partition sums when runs do not tile the partitions */
@@ -517,6 +531,99 @@ __device__ __noinline__ void fb_residual_pass(FbSearchShared<MAXP> &S, const int
 #undef FB_CASE
 }
 
+/*
+ * Costing pass of a whole group over the staged block: every run's window is loaded ONCE and
+ * each member's predictor applied to it (one code path for all members: P covers the highest
+ * order of the group, lower orders have zero coefficients above theirs).  Sums go to the
+ * member's run-sum buffer.  The kernel is bound by instruction fetch and per-run latency, not by
+ * the multiplies: the zero taps are free, the shared window and the single body are not.
+ */
+template <int MAXP, int P, bool WIDE>
+__device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int count,
+                                            const int *ord, unsigned long long *runsum0, int rstride)
+{
+    for (int i0 = (int)threadIdx.x * FB_RUN; i0 < n; i0 += (int)blockDim.x * FB_RUN) {
+        if (i0 + FB_RUN > n) {                                    /* block tail: per member, per sample */
+            for (int m = 0; m < count; m++)
+                fb_run_tail<MAXP>(S, xs, n, ord[m], is_lpc ? ord[m] - 1 : ord[m], n, i0, nullptr, runsum0 + m * rstride, FB_SUMS);
+            continue;
+        }
+        int32_t w[P + FB_RUN];
+#if FB_RUN == 16
+        const fb_sptr xr = fb_to_sptr(xs + fb_skew(i0 + FB_HIST));
+#else
+        const fb_sptr xr = fb_to_sptr(xs);
+#endif
+        FbWindow<P, (P + FB_RUN) / 4>::load(xr, i0 + FB_HIST, w);
+#pragma unroll 1
+        for (int m = 0; m < count; m++) {
+            const int order = ord[m], row = is_lpc ? order - 1 : order;
+            int32_t c[P];
+#pragma unroll
+            for (int g = 0; g < P / 4; g++) {
+                const int4 v = *reinterpret_cast<const int4 *>(&S.coef[row][4 * g]);
+                c[4 * g] = v.x; c[4 * g + 1] = v.y; c[4 * g + 2] = v.z; c[4 * g + 3] = v.w;
+            }
+            const int shift = S.shift[row];
+            unsigned long long acc = 0;
+            uint32_t a32 = 0;
+#pragma unroll
+            for (int k = 0; k < FB_RUN; k++) {
+                int32_t rk;
+                if (WIDE) {
+                    long long pred = 0;
+#pragma unroll
+                    for (int j = 0; j < P; j++) pred += (long long)c[j] * (long long)w[P + k - 1 - j];
+                    rk = (int32_t)((long long)w[P + k] - (pred >> shift));
+                    acc += fb_zigzag(rk);
+                } else {
+                    int32_t pred = 0;
+#pragma unroll
+                    for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
+                    rk = w[P + k] - (pred >> shift);
+                    a32 += fb_zigzag(rk);
+                }
+                if (i0 + k < order) {                             /* warm-up samples are not counted */
+                    if (WIDE) acc -= fb_zigzag(rk); else a32 -= fb_zigzag(rk);
+                }
+            }
+            runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)a32;
+        }
+    }
+}
+
+template <int MAXP>
+__device__ __noinline__ void fb_residual_group(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int count,
+                                               const int *ord, uint32_t maxabs, unsigned long long *runsum0, int rstride)
+{
+    bool narrow = true;
+    int omax = 0;
+    for (int m = 0; m < count; m++) {
+        const int row = is_lpc ? ord[m] - 1 : ord[m];
+        const unsigned long long pm = (unsigned long long)S.sumabs[row] * (unsigned long long)maxabs;
+        narrow = narrow && pm < 0x80000000ull &&
+                 ((unsigned long long)maxabs + (pm >> S.shift[row]) + 1ull) < (1ull << 26);
+        omax = max(omax, ord[m]);
+    }
+    /* one body per kernel for orders up to 12; the order-32 kernel keeps a body per 4 taps */
+    const int P = (MAXP <= 12) ? 12 : ((omax + 3) & ~3);
+#define FB_CASE(PP)                                                                                         \
+    case PP:                                                                                                \
+        if (narrow) fb_tiles_group<MAXP, PP, false>(S, xs, n, is_lpc, count, ord, runsum0, rstride);        \
+        else        fb_tiles_group<MAXP, PP, true>(S, xs, n, is_lpc, count, ord, runsum0, rstride);         \
+        break;
+    if constexpr (MAXP <= 12) {
+        switch (P) { default: FB_CASE(12) }
+    } else {
+        switch (P) {
+            case 0:
+            FB_CASE(4) FB_CASE(8) FB_CASE(12) FB_CASE(16) FB_CASE(20) FB_CASE(24) FB_CASE(28)
+            default: FB_CASE(32)
+        }
+    }
+#undef FB_CASE
+}
+
 /* what a group evaluation needs to know about the subframe */
 struct FbSearchCtx {
     const int32_t *xs;          /* staged plane (fast) */
@@ -533,27 +640,32 @@ struct FbSearchCtx {
  */
 template <int MAXP>
 __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSearchCtx &X, int count, const int *ord,
-                                           int32_t *res_out)
+                                           int32_t *res_out FB_PROF_ARG)
 {
     const int tid = threadIdx.x;
     if (count <= 0) return;
     if (X.fast && X.tileable) {
         unsigned long long *runsum0 = reinterpret_cast<unsigned long long *>(const_cast<int32_t *>(X.xs) + fb_skew_words(X.n));
         const int rstride = fb_runsum_words(X.n) / 2;
-        for (int s = 0; s < count; s++) {
-            const int order = ord[s], row = X.is_lpc ? order - 1 : order;
+        if (res_out) {
+            const int order = ord[0], row = X.is_lpc ? order - 1 : order;
             const int pmax = fb_limit_porder(X.pmax, X.n, order);
-            if (res_out) fb_residual_pass<MAXP, FB_SUMS | FB_STORE>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, res_out, runsum0);
-            else fb_residual_pass<MAXP, FB_SUMS>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, nullptr, runsum0 + s * rstride);
+            fb_residual_pass<MAXP, FB_SUMS | FB_STORE>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, res_out, runsum0);
+        } else {
+            fb_residual_group<MAXP>(S, X.xs, X.n, X.is_lpc, count, ord, X.maxabs, runsum0, rstride);
         }
+        FB_PROF(1);
         __syncthreads();
+        FB_PROF(2);
         for (int s = tid >> 5; s < count; s += (int)(blockDim.x >> 5)) {
             const int order = ord[s];
             const int pmin = fb_limit_porder(X.pmin, X.n, order);
             const int pmax = fb_limit_porder(X.pmax, X.n, order);
             fb_finish_warp<MAXP>(S, s, runsum0 + s * rstride, (X.n >> pmax) / FB_RUN, X.n, X.is_lpc, order, X.obits, pmin, pmax);
         }
+        FB_PROF(3);
         __syncthreads();
+        FB_PROF(4);
         return;
     }
     for (int s = 0; s < count; s++) {
@@ -584,12 +696,15 @@ __device__ __forceinline__ void fb_store_residual(FbSearchShared<MAXP> &S, const
     else        fb_evaluate<MAXP>(S, 0, X.xg, X.n, X.is_lpc, order, row, X.obits, X.pmin, X.pmax, rg, false);
 }
 
+#ifndef FB_SEARCH_MINBLOCKS_WIDE
+#define FB_SEARCH_MINBLOCKS_WIDE 3   /* the order-32 bodies hold a 48-sample window and 32 coefficients */
+#endif
 #ifndef FB_SEARCH_MINBLOCKS
-#define FB_SEARCH_MINBLOCKS 5    /* <= 102 registers: five CTAs per SM; 4 and 6 measured slower */
+#define FB_SEARCH_MINBLOCKS 4    /* <= 128 registers, four CTAs per SM: 3.69 ms per C2 stream; 5 -> 3.79, 6 -> 3.97 (spills) */
 #endif
 
 template <int MAXP>
-__global__ void __launch_bounds__(FB_SEARCH_THREADS, FB_SEARCH_MINBLOCKS)
+__global__ void __launch_bounds__(FB_SEARCH_THREADS, (MAXP > 12 ? FB_SEARCH_MINBLOCKS_WIDE : FB_SEARCH_MINBLOCKS))
 k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
          int32_t *res, FbSub *subs, const int32_t *coefs, const int32_t *shifts, int smem_ints)
 {
@@ -605,6 +720,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     const int n = (int)fr.n;
     FbSub *sb = &subs[sf];
     const int tid = threadIdx.x, T = blockDim.x;
+    FB_PROF_DECL;
     const size_t off = (size_t)fr.start * C + (size_t)c * n;
     const int32_t *xg = smp + off;
     int32_t *rg = res + off;
@@ -653,8 +769,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         if (tid < 5) {
             const int32_t bc[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
             const uint32_t sa[5] = {0, 1, 3, 7, 15};
-#pragma unroll
-            for (int j = 0; j < 4; j++) S.coef[tid][j] = bc[tid][j];
+            for (int j = 0; j < MAXP; j++) S.coef[tid][j] = j < 4 ? bc[tid][j] : 0;   /* bodies may cover more taps */
             S.shift[tid] = 0;
             S.sumabs[tid] = sa[tid];
         }
@@ -665,19 +780,22 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             const int rowi = e / MAXP, j = e % MAXP;
             S.coef[rowi][j] = (rowi < max_order && j <= rowi) ? co[rowi * FB_MAX_ORDER + j] : 0;
         }
-        for (int rowi = tid; rowi < MAXP; rowi += T) {
-            uint32_t sa = 0;
-            if (rowi < max_order)
-                for (int j = 0; j <= rowi; j++) {
-                    const int32_t v = co[rowi * FB_MAX_ORDER + j];
-                    sa += (uint32_t)(v < 0 ? -v : v);                   /* <= 32 * 16383 */
-                }
-            S.sumabs[rowi] = sa;
-            S.shift[rowi] = rowi < max_order ? so[rowi] : 0;
-        }
+        for (int rowi = tid; rowi < MAXP; rowi += T) S.shift[rowi] = rowi < max_order ? so[rowi] : 0;
     }
     if (fast) fb_cp_async_wait_all();
     __syncthreads();
+    if (!fixed) {
+        /* sum |c| per row from the staged rows (a loop of dependent global loads here cost more
+         * than the rest of the staging) */
+        for (int rowi = tid; rowi < MAXP; rowi += T) {
+            uint32_t sa = 0;
+#pragma unroll
+            for (int j = 0; j < MAXP; j++) { const int32_t v = S.coef[rowi][j]; sa += (uint32_t)(v < 0 ? -v : v); }
+            S.sumabs[rowi] = sa;                                    /* <= 32 * 16383 */
+        }
+        __syncthreads();
+    }
+    FB_PROF(0);
 
     int ord[FB_GROUP];
 
@@ -689,7 +807,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         for (int base = min_order; base <= max_order; base += FB_GROUP) {
             int cnt = 0;
             for (int i = base; i <= max_order && cnt < FB_GROUP; i++) ord[cnt++] = i;
-            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
                 if (b < best) { best = b; opt = ord[s]; fb_keep_best<MAXP>(S, s, b); }
@@ -698,7 +816,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         if (best == 0xffffffffu) {      /* min_order > 4 with a tiny last block: undefined in the reference */
             opt = opt > 4 ? 4 : opt;
             ord[0] = opt;
-            fb_eval_group<MAXP>(S, X, 1, ord, rg);
+            fb_eval_group<MAXP>(S, X, 1, ord, rg FB_PROF_PASS);
             fb_keep_best<MAXP>(S, 0, S.result[0]);
         } else {
             fb_store_residual<MAXP>(S, X, opt, rg);
@@ -728,7 +846,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 if (order < 0) order = 0;
                 idx[cnt] = order; ord[cnt] = order + 1; cnt++;
             }
-            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
                 if (b < best) { best = b; opt_order = idx[s]; fb_keep_best<MAXP>(S, s, b); }
@@ -740,7 +858,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         for (int base = 0; base < max_order; base += FB_GROUP) {
             int cnt = 0;
             for (int i = base; i < max_order && cnt < FB_GROUP; i++) ord[cnt++] = i + 1;
-            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
                 if (b < best) { best = b; opt_order = base + s; fb_keep_best<MAXP>(S, s, b); }
@@ -775,7 +893,8 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 for (uint32_t m = cor; m; m &= m - 1) { idx[cnt] = __ffs((int)m) - 1; ord[cnt] = idx[cnt] + 1; cnt++; }
                 gmask |= cor; hyp |= cor; nsteps++;
             }
-            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr);
+            FB_PROF(5);
+            fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             for (int k = 0; k < nsteps; k++, step >>= 1) {
                 const int last = opt_order;
                 for (int i = last - step; i <= last + step; i += step) {
@@ -787,6 +906,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                     if (b < best) { best = b; opt_order = i; fb_keep_best<MAXP>(S, s, b); }
                 }
             }
+            FB_PROF(6);
         }
     }
 
@@ -798,12 +918,17 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         if (tid == 0) { sb->type = 32; sb->order = idx + 1; sb->shift = S.shift[idx]; }
         if (best == 0xffffffffu) {                       /* no search ran (or nothing beat 2^32-1) */
             ord[0] = idx + 1;
-            fb_eval_group<MAXP>(S, X, 1, ord, rg);
+            fb_eval_group<MAXP>(S, X, 1, ord, rg FB_PROF_PASS);
             fb_keep_best<MAXP>(S, 0, S.result[0]);
         } else {
             fb_store_residual<MAXP>(S, X, idx + 1, rg);
         }
+        FB_PROF(7);
         fb_store_best<MAXP>(S, sb);
+        FB_PROF(8);
+#ifdef FB_SEARCH_PROF
+        if (tid == 0) atomicAdd(&g_sprof[15], 1ull);
+#endif
     }
 }
 

@@ -19,7 +19,9 @@
 
 #include "dev_common.cuh"
 
-#define FB_PACK_THREADS 256      /* 59 registers: four CTAs per SM; register caps for 5, 6, 8 measured slower (spills) */
+#define FB_PACK_THREADS 256      /* upper bound; the engine launches 128 for small frames (>= 96 needed: the
+                                  * preamble writers sit at threads 32.. and 64..) */
+/* 59 registers: four CTAs per SM; register caps for 5, 6, 8 measured slower (spills) */
 
 /* ---------------- CRC helpers ---------------------------------------- */
 __device__ __forceinline__ uint32_t fb_crc16_byte(uint32_t crc, uint32_t byte)

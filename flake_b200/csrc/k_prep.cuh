@@ -15,9 +15,11 @@
 
 #include "dev_common.cuh"
 
-#define FB_PREP_THREADS 256
+#ifndef FB_PREP_THREADS
+#define FB_PREP_THREADS 128      /* with 12 CTAs per SM: 0.42 ms per C2 stream; 256 x 6: 0.48; 512 x 3: 0.70 */
+#endif
 #ifndef FB_PREP_MINBLOCKS
-#define FB_PREP_MINBLOCKS 6     /* <= 42 registers, six CTAs per SM: 0.476 ms vs 0.52 (4) and 0.63 (8) per C2 stream */
+#define FB_PREP_MINBLOCKS 12    /* <= 42 registers */
 #endif
 
 /* staging-slot geometry: frame f of a chunk gets a slot that is large enough

@@ -33,11 +33,10 @@ struct FbEngine {
     cudaStream_t stream;
     /* scratch */
     FbFrame *d_frames;
-    uint32_t *d_nframes, *d_verbatim;
+    uint32_t *d_nframes;            /* [0] frame count, [2] k_pack's ticket counter */
     FbSub *d_subs;
     uint8_t *d_modes;
     int32_t *d_smp, *d_res, *d_coefs, *d_shifts;
-    double *d_win;
     uint8_t *d_slots;
     uint32_t *d_frame_len;
     uint64_t *d_frame_off;
@@ -108,7 +107,6 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     const uint64_t nint = e->max_samples * (uint64_t)C;
     FB_TRY_ALLOC(e->d_frames, sizeof(FbFrame) * (size_t)e->max_frames);
     FB_TRY_ALLOC(e->d_nframes, sizeof(uint32_t) * 4);
-    e->d_verbatim = e->d_nframes + 1;
     FB_TRY_ALLOC(e->d_subs, sizeof(FbSub) * (size_t)e->max_subs);
     FB_TRY_ALLOC(e->d_modes, (size_t)e->max_frames);
     FB_TRY_ALLOC(e->d_smp, sizeof(int32_t) * nint);
@@ -179,7 +177,7 @@ extern "C" void fb_engine_destroy(FbEngine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_frames); cudaFree(e->d_nframes); cudaFree(e->d_subs); cudaFree(e->d_modes);
     cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
-    cudaFree(e->d_win); cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
+    cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
     cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32); cudaFree(e->d_crc16tab); cudaFree(e->d_status);
     if (e->tev[0][0])
         for (int p = 0; p < FB_TIMING_RING; p++)

@@ -58,6 +58,7 @@ struct FbSearchShared {
     int32_t  coef[MAXP][MAXP];      /* candidate rows (row = order-1), zero padded */
     int32_t  shift[MAXP];
     uint32_t sumabs[MAXP];          /* sum |coef| per row */
+    uint8_t  pmin_of[MAXP + 1], pmax_of[MAXP + 1];   /* partition-order limits per predictor order (rice.c:148-171) */
     uint32_t result[FB_GROUP];      /* of the group members just finished */
     int32_t  porder[FB_GROUP], method[FB_GROUP];
     int32_t  best_porder, best_method;
@@ -649,7 +650,7 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
         const int rstride = fb_runsum_words(X.n) / 2;
         if (res_out) {
             const int order = ord[0], row = X.is_lpc ? order - 1 : order;
-            const int pmax = fb_limit_porder(X.pmax, X.n, order);
+            const int pmax = S.pmax_of[order];
             fb_residual_pass<MAXP, FB_SUMS | FB_STORE>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, res_out, runsum0);
         } else {
             fb_residual_group<MAXP>(S, X.xs, X.n, X.is_lpc, count, ord, X.maxabs, runsum0, rstride);
@@ -659,8 +660,7 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
         FB_PROF(2);
         for (int s = tid >> 5; s < count; s += (int)(blockDim.x >> 5)) {
             const int order = ord[s];
-            const int pmin = fb_limit_porder(X.pmin, X.n, order);
-            const int pmax = fb_limit_porder(X.pmax, X.n, order);
+            const int pmin = S.pmin_of[order], pmax = S.pmax_of[order];
             fb_finish_warp<MAXP>(S, s, runsum0 + s * rstride, (X.n >> pmax) / FB_RUN, X.n, X.is_lpc, order, X.obits, pmin, pmax);
         }
         FB_PROF(3);
@@ -781,6 +781,10 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             S.coef[rowi][j] = (rowi < max_order && j <= rowi) ? co[rowi * FB_MAX_ORDER + j] : 0;
         }
         for (int rowi = tid; rowi < MAXP; rowi += T) S.shift[rowi] = rowi < max_order ? so[rowi] : 0;
+    }
+    for (int o = tid; o <= MAXP; o += T) {
+        S.pmin_of[o] = (uint8_t)fb_limit_porder(cfg.min_porder, n, o);
+        S.pmax_of[o] = (uint8_t)fb_limit_porder(cfg.max_porder, n, o);
     }
     if (fast) fb_cp_async_wait_all();
     __syncthreads();

@@ -58,6 +58,7 @@ struct FbSearchShared {
     int32_t  coef[MAXP][MAXP];      /* candidate rows (row = order-1), zero padded */
     int32_t  shift[MAXP];
     uint32_t sumabs[MAXP];          /* sum |coef| per row */
+    uint8_t  narrow_of[MAXP];       /* row can be costed in 32-bit arithmetic */
     uint8_t  pmin_of[MAXP + 1], pmax_of[MAXP + 1];   /* partition-order limits per predictor order (rice.c:148-171) */
     uint32_t result[FB_GROUP];      /* of the group members just finished */
     int32_t  porder[FB_GROUP], method[FB_GROUP];
@@ -600,10 +601,7 @@ __device__ __noinline__ void fb_residual_group(FbSearchShared<MAXP> &S, const in
     bool narrow = true;
     int omax = 0;
     for (int m = 0; m < count; m++) {
-        const int row = is_lpc ? ord[m] - 1 : ord[m];
-        const unsigned long long pm = (unsigned long long)S.sumabs[row] * (unsigned long long)maxabs;
-        narrow = narrow && pm < 0x80000000ull &&
-                 ((unsigned long long)maxabs + (pm >> S.shift[row]) + 1ull) < (1ull << 26);
+        narrow = narrow && S.narrow_of[is_lpc ? ord[m] - 1 : ord[m]];
         omax = max(omax, ord[m]);
     }
     /* one body per kernel for orders up to 12; the order-32 kernel keeps a body per 4 taps */
@@ -772,6 +770,8 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             for (int j = 0; j < MAXP; j++) S.coef[tid][j] = j < 4 ? bc[tid][j] : 0;   /* bodies may cover more taps */
             S.shift[tid] = 0;
             S.sumabs[tid] = sa[tid];
+            S.narrow_of[tid] = (unsigned long long)sa[tid] * sb->maxabs < 0x80000000ull &&
+                               ((unsigned long long)sb->maxabs + (unsigned long long)sa[tid] * sb->maxabs + 1ull) < (1ull << 26);
         }
     } else {
         const int32_t *co = coefs + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
@@ -796,6 +796,9 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
 #pragma unroll
             for (int j = 0; j < MAXP; j++) { const int32_t v = S.coef[rowi][j]; sa += (uint32_t)(v < 0 ? -v : v); }
             S.sumabs[rowi] = sa;                                    /* <= 32 * 16383 */
+            const unsigned long long pm = (unsigned long long)sa * (unsigned long long)sb->maxabs;
+            S.narrow_of[rowi] = pm < 0x80000000ull &&
+                                ((unsigned long long)sb->maxabs + (pm >> S.shift[rowi]) + 1ull) < (1ull << 26);
         }
         __syncthreads();
     }

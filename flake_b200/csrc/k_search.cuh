@@ -815,10 +815,12 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             int cnt = 0;
             for (int i = base; i <= max_order && cnt < FB_GROUP; i++) ord[cnt++] = i;
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
+            int bs = -1;
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
-                if (b < best) { best = b; opt = ord[s]; fb_keep_best<MAXP>(S, s, b); }
+                if (b < best) { best = b; opt = ord[s]; bs = s; }
             }
+            if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);       /* one copy per group: only the last winner matters */
         }
         if (best == 0xffffffffu) {      /* min_order > 4 with a tiny last block: undefined in the reference */
             opt = opt > 4 ? 4 : opt;
@@ -854,10 +856,12 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 idx[cnt] = order; ord[cnt] = order + 1; cnt++;
             }
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
+            int bs = -1;
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
-                if (b < best) { best = b; opt_order = idx[s]; fb_keep_best<MAXP>(S, s, b); }
+                if (b < best) { best = b; opt_order = idx[s]; bs = s; }
             }
+            if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);
         }
     } else if (om == 5) {
         /* optimize.c:223-240: every order */
@@ -866,10 +870,12 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             int cnt = 0;
             for (int i = base; i < max_order && cnt < FB_GROUP; i++) ord[cnt++] = i + 1;
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
+            int bs = -1;
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
-                if (b < best) { best = b; opt_order = base + s; fb_keep_best<MAXP>(S, s, b); }
+                if (b < best) { best = b; opt_order = base + s; bs = s; }
             }
+            if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);
         }
     } else {
         /* log search, optimize.c:241-261.  A step's candidates are last-step, last, last+step.
@@ -902,6 +908,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             }
             FB_PROF(5);
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
+            int bs = -1;
             for (int k = 0; k < nsteps; k++, step >>= 1) {
                 const int last = opt_order;
                 for (int i = last - step; i <= last + step; i += step) {
@@ -910,9 +917,10 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                     for (int q = 1; q < FB_GROUP; q++) if (q < cnt && idx[q] == i) s = q;
                     const uint32_t b = S.result[s];
                     done |= 1u << i;
-                    if (b < best) { best = b; opt_order = i; fb_keep_best<MAXP>(S, s, b); }
+                    if (b < best) { best = b; opt_order = i; bs = s; }
                 }
             }
+            if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);
             FB_PROF(6);
         }
     }

@@ -638,7 +638,7 @@ struct FbSearchCtx {
  * stores the residual -- the orders that are not searched (optimize.c:196-204) need one pass.
  */
 template <int MAXP>
-__device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSearchCtx &X, int count, const int *ord,
+__device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSearchCtx X, int count, const int *ord,
                                            int32_t *res_out FB_PROF_ARG)
 {
     const int tid = threadIdx.x;
@@ -687,7 +687,7 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
 
 /* residual of the chosen predictor to global memory (optimize.c:266-275), no costing */
 template <int MAXP>
-__device__ __forceinline__ void fb_store_residual(FbSearchShared<MAXP> &S, const FbSearchCtx &X, int order, int32_t *rg)
+__device__ __forceinline__ void fb_store_residual(FbSearchShared<MAXP> &S, const FbSearchCtx X, int order, int32_t *rg)
 {
     const int row = X.is_lpc ? order - 1 : order;
     if (X.fast) fb_residual_pass<MAXP, FB_STORE>(S, X.xs, X.n, order, row, X.n, X.maxabs, rg, nullptr);

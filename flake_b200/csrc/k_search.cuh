@@ -533,6 +533,12 @@ __device__ __noinline__ void fb_residual_pass(FbSearchShared<MAXP> &S, const int
 #undef FB_CASE
 }
 
+/* the orders of a group's members, 8 bits each (orders <= 32): travels in a register, where an
+ * int array would live in local memory */
+typedef uint32_t FbOrders;
+__device__ __forceinline__ int fb_order_of(FbOrders o, int m) { return (int)((o >> (8 * m)) & 0xffu); }
+__device__ __forceinline__ FbOrders fb_order_put(FbOrders o, int m, int order) { return o | ((FbOrders)order << (8 * m)); }
+
 /*
  * Costing pass of a whole group over the staged block: every run's window is loaded ONCE and
  * each member's predictor applied to it (one code path for all members: P covers the highest
@@ -542,12 +548,12 @@ __device__ __noinline__ void fb_residual_pass(FbSearchShared<MAXP> &S, const int
  */
 template <int MAXP, int P, bool WIDE>
 __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int count,
-                                            const int *ord, unsigned long long *runsum0, int rstride)
+                                            FbOrders ord, unsigned long long *runsum0, int rstride)
 {
     for (int i0 = (int)threadIdx.x * FB_RUN; i0 < n; i0 += (int)blockDim.x * FB_RUN) {
         if (i0 + FB_RUN > n) {                                    /* block tail: per member, per sample */
             for (int m = 0; m < count; m++)
-                fb_run_tail<MAXP>(S, xs, n, ord[m], is_lpc ? ord[m] - 1 : ord[m], n, i0, nullptr, runsum0 + m * rstride, FB_SUMS);
+                fb_run_tail<MAXP>(S, xs, n, fb_order_of(ord, m), is_lpc ? fb_order_of(ord, m) - 1 : fb_order_of(ord, m), n, i0, nullptr, runsum0 + m * rstride, FB_SUMS);
             continue;
         }
         int32_t w[P + FB_RUN];
@@ -559,7 +565,7 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
         FbWindow<P, (P + FB_RUN) / 4>::load(xr, i0 + FB_HIST, w);
 #pragma unroll 1
         for (int m = 0; m < count; m++) {
-            const int order = ord[m], row = is_lpc ? order - 1 : order;
+            const int order = fb_order_of(ord, m), row = is_lpc ? order - 1 : order;
             int32_t c[P];
 #pragma unroll
             for (int g = 0; g < P / 4; g++) {
@@ -596,13 +602,14 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
 
 template <int MAXP>
 __device__ __noinline__ void fb_residual_group(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int count,
-                                               const int *ord, uint32_t maxabs, unsigned long long *runsum0, int rstride)
+                                               FbOrders ord, uint32_t maxabs, unsigned long long *runsum0, int rstride)
 {
     bool narrow = true;
     int omax = 0;
     for (int m = 0; m < count; m++) {
-        narrow = narrow && S.narrow_of[is_lpc ? ord[m] - 1 : ord[m]];
-        omax = max(omax, ord[m]);
+        const int order = fb_order_of(ord, m);
+        narrow = narrow && S.narrow_of[is_lpc ? order - 1 : order];
+        omax = max(omax, order);
     }
     /* one body per kernel for orders up to 12; the order-32 kernel keeps a body per 4 taps */
     const int P = (MAXP <= 12) ? 12 : ((omax + 3) & ~3);
@@ -638,7 +645,7 @@ struct FbSearchCtx {
  * stores the residual -- the orders that are not searched (optimize.c:196-204) need one pass.
  */
 template <int MAXP>
-__device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSearchCtx X, int count, const int *ord,
+__device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSearchCtx X, int count, FbOrders ord,
                                            int32_t *res_out FB_PROF_ARG)
 {
     const int tid = threadIdx.x;
@@ -647,7 +654,7 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
         unsigned long long *runsum0 = reinterpret_cast<unsigned long long *>(const_cast<int32_t *>(X.xs) + fb_skew_words(X.n));
         const int rstride = fb_runsum_words(X.n) / 2;
         if (res_out) {
-            const int order = ord[0], row = X.is_lpc ? order - 1 : order;
+            const int order = fb_order_of(ord, 0), row = X.is_lpc ? order - 1 : order;
             const int pmax = S.pmax_of[order];
             fb_residual_pass<MAXP, FB_SUMS | FB_STORE>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, res_out, runsum0);
         } else {
@@ -657,7 +664,7 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
         __syncthreads();
         FB_PROF(2);
         for (int s = tid >> 5; s < count; s += (int)(blockDim.x >> 5)) {
-            const int order = ord[s];
+            const int order = fb_order_of(ord, s);
             const int pmin = S.pmin_of[order], pmax = S.pmax_of[order];
             fb_finish_warp<MAXP>(S, s, runsum0 + s * rstride, (X.n >> pmax) / FB_RUN, X.n, X.is_lpc, order, X.obits, pmin, pmax);
         }
@@ -667,7 +674,7 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
         return;
     }
     for (int s = 0; s < count; s++) {
-        const int order = ord[s], row = X.is_lpc ? order - 1 : order;
+        const int order = fb_order_of(ord, s), row = X.is_lpc ? order - 1 : order;
         if (X.fast) {
             const int pmin = fb_limit_porder(X.pmin, X.n, order);
             const int pmax = fb_limit_porder(X.pmax, X.n, order);
@@ -804,7 +811,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     }
     FB_PROF(0);
 
-    int ord[FB_GROUP];
+    FbOrders ord;
 
     /* FIXED, optimize.c:168-190: row = order (row 0 is the all-zero order-0 predictor) */
     if (fixed) {
@@ -813,18 +820,19 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         uint32_t best = 0xffffffffu;
         for (int base = min_order; base <= max_order; base += FB_GROUP) {
             int cnt = 0;
-            for (int i = base; i <= max_order && cnt < FB_GROUP; i++) ord[cnt++] = i;
+            ord = 0;
+            for (int i = base; i <= max_order && cnt < FB_GROUP; i++) ord = fb_order_put(ord, cnt++, i);
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             int bs = -1;
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
-                if (b < best) { best = b; opt = ord[s]; bs = s; }
+                if (b < best) { best = b; opt = fb_order_of(ord, s); bs = s; }
             }
             if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);       /* one copy per group: only the last winner matters */
         }
         if (best == 0xffffffffu) {      /* min_order > 4 with a tiny last block: undefined in the reference */
             opt = opt > 4 ? 4 : opt;
-            ord[0] = opt;
+            ord = (FbOrders)opt;
             fb_eval_group<MAXP>(S, X, 1, ord, rg FB_PROF_PASS);
             fb_keep_best<MAXP>(S, 0, S.result[0]);
         } else {
@@ -849,17 +857,18 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         const int levels = 1 << (om - 1);
         opt_order = max_order - 1;
         for (int base = levels - 1; base >= 0; base -= FB_GROUP) {
-            int cnt = 0, idx[FB_GROUP];
+            int cnt = 0;
+            ord = 0;
             for (int i = base; i >= 0 && cnt < FB_GROUP; i--) {
                 int order = min_order + (((max_order - min_order + 1) * (i + 1)) / levels) - 2;
                 if (order < 0) order = 0;
-                idx[cnt] = order; ord[cnt] = order + 1; cnt++;
+                ord = fb_order_put(ord, cnt, order + 1); cnt++;
             }
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             int bs = -1;
             for (int s = 0; s < cnt; s++) {
                 const uint32_t b = S.result[s];
-                if (b < best) { best = b; opt_order = idx[s]; bs = s; }
+                if (b < best) { best = b; opt_order = fb_order_of(ord, s) - 1; bs = s; }
             }
             if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);
         }
@@ -868,7 +877,8 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         opt_order = 0;
         for (int base = 0; base < max_order; base += FB_GROUP) {
             int cnt = 0;
-            for (int i = base; i < max_order && cnt < FB_GROUP; i++) ord[cnt++] = i + 1;
+            ord = 0;
+            for (int i = base; i < max_order && cnt < FB_GROUP; i++) ord = fb_order_put(ord, cnt++, i + 1);
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             int bs = -1;
             for (int s = 0; s < cnt; s++) {
@@ -887,7 +897,8 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         opt_order = lo + (max_order - min_order) / 3;
         int step = 16;
         while (step > 0) {
-            int cnt = 0, idx[FB_GROUP], nsteps = 0;
+            int cnt = 0, nsteps = 0;
+            ord = 0;
             uint32_t gmask = 0, hyp = 1u << opt_order;
             const int lane = tid & 31;
             const uint32_t range = (hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
@@ -903,7 +914,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 const uint32_t cor = __reduce_or_sync(FB_FULL_MASK, live ? cm : 0u);
                 const uint32_t cand = __reduce_and_sync(FB_FULL_MASK, live ? cm : 0xffffffffu);
                 if (cor != cand || cnt + __popc(cor) > FB_GROUP) break;
-                for (uint32_t m = cor; m; m &= m - 1) { idx[cnt] = __ffs((int)m) - 1; ord[cnt] = idx[cnt] + 1; cnt++; }
+                for (uint32_t m = cor; m; m &= m - 1) { ord = fb_order_put(ord, cnt, __ffs((int)m)); cnt++; }
                 gmask |= cor; hyp |= cor; nsteps++;
             }
             FB_PROF(5);
@@ -914,7 +925,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 for (int i = last - step; i <= last + step; i += step) {
                     if (i < lo || i > hi || ((done >> i) & 1u)) continue;
                     int s = 0;
-                    for (int q = 1; q < FB_GROUP; q++) if (q < cnt && idx[q] == i) s = q;
+                    for (int q = 1; q < FB_GROUP; q++) if (q < cnt && fb_order_of(ord, q) == i + 1) s = q;
                     const uint32_t b = S.result[s];
                     done |= 1u << i;
                     if (b < best) { best = b; opt_order = i; bs = s; }
@@ -932,7 +943,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         if (tid < FB_MAX_ORDER) sb->coefs[tid] = (tid <= idx && tid < MAXP) ? S.coef[idx][tid] : 0;
         if (tid == 0) { sb->type = 32; sb->order = idx + 1; sb->shift = S.shift[idx]; }
         if (best == 0xffffffffu) {                       /* no search ran (or nothing beat 2^32-1) */
-            ord[0] = idx + 1;
+            ord = (FbOrders)(idx + 1);
             fb_eval_group<MAXP>(S, X, 1, ord, rg FB_PROF_PASS);
             fb_keep_best<MAXP>(S, 0, S.result[0]);
         } else {

@@ -182,6 +182,32 @@ __device__ __forceinline__ int fb_rice_k(uint64_t sum, int n)
     return fb_rice_k_scan(sum, n);
 }
 
+/* the same two for sums known to be below 2^31 (and n <= 65535): all 32-bit.  `sum - n/2` is
+ * negative only where k == 0, where wrapping modulo 2^32 equals the reference's 64-bit wrap
+ * truncated to uint32. */
+__device__ __forceinline__ int fb_rice_k_t(uint32_t sum, int n)
+{
+    const int s = (int)sum - (n >> 1);
+    const int t = 2 * n;
+    if (s <= t) return 0;
+    int k = __clz(t) - __clz(s);                        /* 0 <= t < s < 2^31 */
+    if (k < 0) k = 0;
+    if ((s >> k) > t) k++;
+    return k > 30 ? 30 : k;
+}
+
+__device__ __forceinline__ uint32_t fb_rice_count_t(uint32_t sum, int n, int k)
+{
+    return (uint32_t)(n * (k + 1)) + ((sum - (uint32_t)(n >> 1)) >> k);
+}
+
+__device__ __forceinline__ int fb_rice_k_t(unsigned long long sum, int n) { return fb_rice_k((uint64_t)sum, n); }
+
+__device__ __forceinline__ uint32_t fb_rice_count_t(unsigned long long sum, int n, int k)
+{
+    return (uint32_t)fb_rice_count64((uint64_t)sum, n, k);
+}
+
 /* rice.c:148-155 */
 __device__ __forceinline__ int fb_limit_porder(int p, int n, int order)
 {

@@ -104,8 +104,8 @@ __device__ __forceinline__ int32_t fb_lpc_residual(const int32_t *x, int i, int 
  * Posts S.result[slot] (rice.c:157-187 total), S.porder[slot], S.method[slot] and the
  * parameters of every level in S.kbuf[slot].
  */
-template <int MAXP>
-__device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, const unsigned long long *F,
+template <int MAXP, typename SumT>
+__device__ __forceinline__ void fb_finish_body(FbSearchShared<MAXP> &S, int slot, const unsigned long long *F,
                                                int per, int n, int is_lpc, int order, int obits,
                                                int pmin, int pmax)
 {
@@ -113,7 +113,7 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
     uint8_t *kbuf = S.kbuf[slot];
     uint32_t best = 0xffffffffu;
     int bl = pmin, bmethod = 0;
-    unsigned long long t5 = 0;
+    SumT t5 = 0;
 
     /* levels with 32 partitions or more */
 #pragma unroll 1
@@ -124,13 +124,13 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
 #pragma unroll 1
         for (int j = lane; j < (1 << L); j += 32) {
             const unsigned long long *src = F + j * span;
-            unsigned long long sum = 0;
+            SumT sum = 0;
 #pragma unroll 4
-            for (int q = 0; q < span; q++) sum += src[q];
+            for (int q = 0; q < span; q++) sum += (SumT)src[q];
             const int cnt = (n >> L) - (j == 0 ? order : 0);
-            const int k = fb_rice_k(sum, cnt);
+            const int k = fb_rice_k_t(sum, cnt);
             kbuf[(1 << L) - 1 + j] = (uint8_t)k;
-            bits += (uint32_t)fb_rice_count64(sum, cnt, k);
+            bits += fb_rice_count_t(sum, cnt, k);
             flag |= (k > 14);
             t5 = sum;                                     /* L == 5: the lane's own partition */
         }
@@ -142,8 +142,8 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
     if (pmax < 5) {
         /* the lanes of a group share partition lane / g of level pmax */
         const int g = 32 >> pmax, j = lane / g, sub = lane % g;
-        unsigned long long a = 0;
-        for (int q = sub; q < per; q += g) a += F[j * per + q];
+        SumT a = 0;
+        for (int q = sub; q < per; q += g) a += (SumT)F[j * per + q];
         for (int o = 1; o < g; o <<= 1) a += __shfl_xor_sync(FB_FULL_MASK, a, o);
         t5 = a;
     }
@@ -151,15 +151,15 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
     /* levels 4..0 (and level pmax < 5): t[L] = sum of the partition this lane belongs to.
      * With pmax < 5 the lanes start out holding level pmax, so the merges above it are skipped. */
     if (pmin < 5) {
-        unsigned long long t[5];
+        SumT t[5];
         {
-            const unsigned long long o = __shfl_xor_sync(FB_FULL_MASK, t5, 1);
-            t[4] = t5 + (5 <= pmax ? o : 0ull);
+            const SumT o = __shfl_xor_sync(FB_FULL_MASK, t5, 1);
+            t[4] = t5 + (5 <= pmax ? o : (SumT)0);
         }
 #pragma unroll
         for (int L = 4; L >= 1; L--) {
-            const unsigned long long o = __shfl_xor_sync(FB_FULL_MASK, t[L], 1 << (5 - L));
-            t[L - 1] = t[L] + (L <= pmax ? o : 0ull);
+            const SumT o = __shfl_xor_sync(FB_FULL_MASK, t[L], 1 << (5 - L));
+            t[L - 1] = t[L] + (L <= pmax ? o : (SumT)0);
         }
         uint32_t bits[5];
         int ks[5];
@@ -167,10 +167,10 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
         for (int L = 0; L < 5; L++) {
             const int g = 32 >> L, j = lane / g;
             const int cnt = (n >> L) - (j == 0 ? order : 0);
-            const int k = fb_rice_k(t[L], cnt);
+            const int k = fb_rice_k_t(t[L], cnt);
             const bool mine = (lane % g) == 0 && L <= pmax && L >= pmin;
             ks[L] = k;
-            bits[L] = mine ? (uint32_t)fb_rice_count64(t[L], cnt, k) : 0u;
+            bits[L] = mine ? fb_rice_count_t(t[L], cnt, k) : 0u;
         }
 #pragma unroll
         for (int L = 4; L >= 0; L--) {
@@ -193,6 +193,38 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
         S.porder[slot] = bl;
         S.method[slot] = bmethod;
     }
+}
+
+
+/* the always-exact 64-bit finish, out of line: audio whose zig-zag residuals sum to 2^31 or more
+ * over one block (mean |residual| of 2^18 at 4096 samples) is the rare case */
+template <int MAXP>
+__device__ __noinline__ void fb_finish_wide(FbSearchShared<MAXP> &S, int slot, const unsigned long long *F,
+                                            int per, int n, int is_lpc, int order, int obits, int pmin, int pmax)
+{
+    fb_finish_body<MAXP, unsigned long long>(S, slot, F, per, n, is_lpc, order, obits, pmin, pmax);
+}
+
+/*
+ * One whole warp.  When every entry of F is below 2^31 / entries, every partition sum of every
+ * level is below 2^31 and the whole finish is exact in 32-bit arithmetic (the costs are uint32
+ * in the reference, rice.c:30-45, and `sum - n/2` can only wrap where k = 0, where the wrap is
+ * the same modulo 2^32); otherwise the 64-bit body.
+ */
+template <int MAXP>
+__device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, const unsigned long long *F,
+                                            int per, int n, int is_lpc, int order, int obits, int pmin, int pmax)
+{
+    const int nent = per << pmax;                                   /* entries of F, <= 4096 */
+    const int rs = 31 - (32 - __clz(nent - 1 | 1));                 /* entries < 2^rs  =>  total < 2^31 */
+    unsigned long long hi = 0;
+#pragma unroll 4
+    for (int q = threadIdx.x & 31; q < nent; q += 32) hi |= F[q] >> rs;
+    if (__any_sync(FB_FULL_MASK, hi != 0)) {
+        fb_finish_wide<MAXP>(S, slot, F, per, n, is_lpc, order, obits, pmin, pmax);
+        return;
+    }
+    fb_finish_body<MAXP, uint32_t>(S, slot, F, per, n, is_lpc, order, obits, pmin, pmax);
 }
 
 /* group member `slot` is the best candidate so far: warp 0 keeps its parameters */

@@ -605,6 +605,7 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
                 c[4 * g] = v.x; c[4 * g + 1] = v.y; c[4 * g + 2] = v.z; c[4 * g + 3] = v.w;
             }
             const int shift = S.shift[row];
+            const int wlim = order - i0;                          /* samples of this run below the order */
             unsigned long long acc = 0;
             uint32_t a32 = 0;
 #pragma unroll
@@ -623,7 +624,7 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
                     rk = w[P + k] - (pred >> shift);
                     a32 += fb_zigzag(rk);
                 }
-                if (i0 + k < order) {                             /* warm-up samples are not counted */
+                if (k < P && k < wlim) {                          /* warm-up samples are not counted (order <= P) */
                     if (WIDE) acc -= fb_zigzag(rk); else a32 -= fb_zigzag(rk);
                 }
             }

@@ -622,13 +622,14 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
 #pragma unroll
                     for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
                     rk = w[P + k] - (pred >> shift);
-                    a32 += fb_zigzag(rk);
+                    /* zigzag(r) = (|4r + 1| - 1) / 2, |r| < 2^26: the sum of sixteen |4r + 1| fits 32 bits;
+                     * a warm-up sample (order <= P) counts as r = 0 */
+                    if (k < P && k < wlim) rk = 0;
+                    a32 += (uint32_t)abs(4 * rk + 1);
                 }
-                if (k < P && k < wlim) {                          /* warm-up samples are not counted (order <= P) */
-                    if (WIDE) acc -= fb_zigzag(rk); else a32 -= fb_zigzag(rk);
-                }
+                if (WIDE && k < P && k < wlim) acc -= fb_zigzag(rk);   /* warm-up samples are not counted */
             }
-            runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)a32;
+            runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)((a32 - FB_RUN) >> 1);
         }
     }
 }

@@ -402,9 +402,13 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
                         /* a short rolled body: the kernel is bound by instruction fetch (the fully
                          * unrolled 16 codes cost 1.68 ms per C2 stream against 1.41) */
 #if FB_PACK_EMIT_UNROLL == 4
+                        /* the next four samples are requested before the current four are coded: the
+                         * emitter's stores may alias the source as far as the compiler knows */
+                        int4 nxt = src[0];
 #pragma unroll 1
                         for (int g = 0; g < 4; g++) {
-                            const int4 v = src[g];
+                            const int4 v = nxt;
+                            if (g < 3) nxt = src[g + 1];
                             fb_bp_put_rice(b, fb_zigzag(v.x), k); fb_bp_put_rice(b, fb_zigzag(v.y), k);
                             fb_bp_put_rice(b, fb_zigzag(v.z), k); fb_bp_put_rice(b, fb_zigzag(v.w), k);
                         }

@@ -754,19 +754,24 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     const uint32_t sf = blockIdx.x;
     const uint32_t f = sf / (uint32_t)C;
     const int c = (int)(sf % (uint32_t)C);
-    if (f >= *nframes) return;
-    const FbFrame fr = frames[f];
-    const int n = (int)fr.n;
+    /* the grid never exceeds the frame table (engine.cu sizes both for the same upper bound), so the
+     * records are requested together with the frame count instead of one round trip later */
     FbSub *sb = &subs[sf];
+    const uint32_t nf = *nframes;
+    const FbFrame fr = frames[f];
+    const int sb_obits = sb->obits, sb_const = sb->is_const;
+    const uint32_t sb_maxabs = sb->maxabs;
+    if (f >= nf) return;
+    const int n = (int)fr.n;
     const int tid = threadIdx.x, T = blockDim.x;
     FB_PROF_DECL;
     const size_t off = (size_t)fr.start * C + (size_t)c * n;
     const int32_t *xg = smp + off;
     int32_t *rg = res + off;
-    const int obits = sb->obits;
+    const int obits = sb_obits;
 
     /* CONSTANT, optimize.c:143-151 */
-    if (sb->is_const) {
+    if (sb_const) {
         if (tid == 0) { sb->type = 0; sb->order = 0; sb->est_bits = (uint32_t)obits; }
         return;
     }
@@ -795,7 +800,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     FbSearchCtx X;
     X.xs = xs; X.xg = xg; X.n = n; X.obits = obits;
     X.pmin = cfg.min_porder; X.pmax = cfg.max_porder; X.is_lpc = fixed ? 0 : 1;
-    X.maxabs = sb->maxabs; X.fast = fast;
+    X.maxabs = sb_maxabs; X.fast = fast;
     {
         /* the finest partition any candidate can use: larger ones are multiples of it */
         const int pfin = fb_limit_porder(cfg.max_porder, n, 0);
@@ -811,8 +816,8 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             for (int j = 0; j < MAXP; j++) S.coef[tid][j] = j < 4 ? bc[tid][j] : 0;   /* bodies may cover more taps */
             S.shift[tid] = 0;
             S.sumabs[tid] = sa[tid];
-            S.narrow_of[tid] = (unsigned long long)sa[tid] * sb->maxabs < 0x80000000ull &&
-                               ((unsigned long long)sb->maxabs + (unsigned long long)sa[tid] * sb->maxabs + 1ull) < (1ull << 26);
+            S.narrow_of[tid] = (unsigned long long)sa[tid] * sb_maxabs < 0x80000000ull &&
+                               ((unsigned long long)sb_maxabs + (unsigned long long)sa[tid] * sb_maxabs + 1ull) < (1ull << 26);
         }
     } else {
         const int32_t *co = coefs + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
@@ -837,9 +842,9 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
 #pragma unroll
             for (int j = 0; j < MAXP; j++) { const int32_t v = S.coef[rowi][j]; sa += (uint32_t)(v < 0 ? -v : v); }
             S.sumabs[rowi] = sa;                                    /* <= 32 * 16383 */
-            const unsigned long long pm = (unsigned long long)sa * (unsigned long long)sb->maxabs;
+            const unsigned long long pm = (unsigned long long)sa * (unsigned long long)sb_maxabs;
             S.narrow_of[rowi] = pm < 0x80000000ull &&
-                                ((unsigned long long)sb->maxabs + (pm >> S.shift[rowi]) + 1ull) < (1ull << 26);
+                                ((unsigned long long)sb_maxabs + (pm >> S.shift[rowi]) + 1ull) < (1ull << 26);
         }
         __syncthreads();
     }

@@ -31,6 +31,8 @@ CASES = [
     ("l12_s24", 2048, 2, 24, 96000, "mix", 12, {"block_size": 2048}),
     ("l9_3ch", 1024 + 256, 3, 24, 48000, "impulses", 9, {"block_size": 1024}),
     ("noise_l0", 1152, 2, 16, 44100, "noise", 0, {}),
+    # full-scale 24-bit noise: run sums of 2^28, partition sums beyond 2^32 -> the 64-bit finish of k_search
+    ("noise_s24_l8", 1024 * 2, 2, 24, 96000, "noise", 8, {"block_size": 1024}),
     ("wasted_l5", 1024, 2, 16, 44100, "wasted", 5, {"block_size": 1024}),
     ("silence_l8", 1024, 2, 16, 44100, "silence", 8, {"block_size": 1024}),
 ]

@@ -32,6 +32,9 @@ CASES = [
     ("l8_mono",  4096 * 3 + 10, 1, 16, 44100, "mix", 8, {}),
     ("l8_noise", 4096 * 3, 2, 16, 44100, "noise", 8, {}),
     ("l0_noise", 1152 * 5, 2, 16, 44100, "noise", 0, {}),
+    # full-scale 24-bit noise: zig-zag totals beyond 2^32 per block -> the 64-bit finish of k_search
+    ("l8_noise_s24", 4096 * 3, 2, 24, 96000, "noise", 8, {}),
+    ("l12_noise_s24", 8192 * 2, 2, 24, 96000, "noise", 12, {}),
     ("l5_wasted", 4096 * 3, 2, 16, 44100, "wasted", 5, {}),
     ("l5_silence", 4096 * 3, 2, 16, 44100, "silence", 5, {}),
     ("l8_tiny_tail", 4096 + 7, 2, 16, 44100, "mix", 8, {}),

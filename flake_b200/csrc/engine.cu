@@ -125,7 +125,12 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     }
 
     /* shared-memory staging where a whole block fits */
-    e->search_smem_ints = ((size_t)fb_search_smem_words(B) * 4 <= FB_SMEM_BUDGET) ? fb_search_smem_words(B) : 0;
+    {
+        /* the kernel this configuration launches (dispatch in fb_engine_encode_device) */
+        const int group = (cfg->prediction_type == 2 && cfg->max_order > 12) ? FB_GROUP_OF(32) : FB_GROUP_OF(12);
+        const int words = fb_search_smem_words(B, group);
+        e->search_smem_ints = ((size_t)words * 4 <= FB_SMEM_BUDGET) ? words : 0;
+    }
     {
         const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
         const uint64_t capw = (capb + 3u) >> 2;

@@ -8,7 +8,7 @@
  * parameter per partition (rice.c:30-74) and the smallest total over the
  * allowed partition orders with ties going to the HIGHER order (rice.c:128-135).
  *
- * Candidates are evaluated in GROUPS of up to three whose members do not depend on
+ * Candidates are evaluated in GROUPS of up to three (order-32 kernel: four; one finishing warp each) whose members do not depend on
  * each other's result (the order searches of optimize.c:205-261 are replayed on
  * the stored costs afterwards, so the decisions are the reference's):
  *   tiles     for each member, every thread owns 16-sample runs; the run and its
@@ -34,7 +34,12 @@
 #define FB_SEARCH_THREADS 128    /* 16 samples per thread and tile; measured best of 64/96/128/256 on B200 */
 #endif
 
-#define FB_GROUP 3                  /* candidates evaluated between two decisions */
+/* Candidates evaluated between two decisions, one finishing warp each (at most 4: FbOrders).
+ * The order <= 12 kernel takes three: its usual search (log, C2) never has more than three
+ * independent candidates and the fourth run-sum array only costs shared memory (3.174 vs 3.187 ms);
+ * the order-32 kernel takes four (exhaustive search of C3: 6.02 -> 5.56 ms). */
+#define FB_GROUP_MAX 4
+#define FB_GROUP_OF(MAXP) ((MAXP) > 12 ? 4 : 3)
 
 /* dev builds (-DFB_SEARCH_PROF): cycles per phase as seen by thread 0, summed over all CTAs */
 #ifdef FB_SEARCH_PROF
@@ -53,15 +58,15 @@ __device__ unsigned long long g_sprof[16];
 template <int MAXP>
 struct FbSearchShared {
     unsigned long long sums[256];   /* finest-level partition sums when runs do not tile the partitions */
-    uint8_t  kbuf[FB_GROUP][512];   /* group member: parameter of partition j at level L at [(1<<L)-1+j] */
+    uint8_t  kbuf[FB_GROUP_OF(MAXP)][512];   /* group member: parameter of partition j at level L at [(1<<L)-1+j] */
     uint8_t  kbest[256];            /* best candidate so far: parameters at its partition order */
     int32_t  coef[MAXP][MAXP];      /* candidate rows (row = order-1), zero padded */
     int32_t  shift[MAXP];
     uint32_t sumabs[MAXP];          /* sum |coef| per row */
     uint8_t  narrow_of[MAXP];       /* row can be costed in 32-bit arithmetic */
     uint8_t  pmin_of[MAXP + 1], pmax_of[MAXP + 1];   /* partition-order limits per predictor order (rice.c:148-171) */
-    uint32_t result[FB_GROUP];      /* of the group members just finished */
-    int32_t  porder[FB_GROUP], method[FB_GROUP];
+    uint32_t result[FB_GROUP_MAX];      /* of the group members just finished */
+    int32_t  porder[FB_GROUP_MAX], method[FB_GROUP_MAX];
     int32_t  best_porder, best_method;
     uint32_t best_bits;
 };
@@ -325,7 +330,7 @@ __host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n
 /* 64-bit zig-zag sums, one per 16-sample run, per group member: words */
 __host__ __device__ __forceinline__ int fb_runsum_words(int n) { return 2 * (((n + FB_RUN - 1) / FB_RUN) + 2); }
 /* staged plane + the run sums of a whole group, in 32-bit words */
-__host__ __device__ __forceinline__ int fb_search_smem_words(int n) { return fb_skew_words(n) + FB_GROUP * fb_runsum_words(n); }
+__host__ __device__ __forceinline__ int fb_search_smem_words(int n, int group) { return fb_skew_words(n) + group * fb_runsum_words(n); }
 /* word offset of logical (16 m + d) relative to that of logical 16 m; d may be negative */
 __host__ __device__ constexpr int fb_skew_delta(int d) { return d + 4 * (d >= 0 ? d / 16 : -((-d + 15) / 16)); }
 
@@ -674,7 +679,7 @@ struct FbSearchCtx {
 };
 
 /*
- * Cost `count` (<= FB_GROUP) candidates of orders ord[]; totals land in S.result[0..count).
+ * Cost `count` (<= FB_GROUP_OF(MAXP)) candidates of orders ord[]; totals land in S.result[0..count).
  * Every thread of the CTA calls it.  res_out != NULL (count == 1 only): the same pass also
  * stores the residual -- the orders that are not searched (optimize.c:196-204) need one pass.
  */
@@ -782,7 +787,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     }
 
     /* stage the plane: skewed layout, FB_HIST zero samples in front (fast path) */
-    const bool fast = fb_search_smem_words(n) <= smem_ints;
+    const bool fast = fb_search_smem_words(n, FB_GROUP_OF(MAXP)) <= smem_ints;
     int32_t *xs = (int32_t *)dyn;
     if (fast) {
         for (int L = tid; L < FB_HIST; L += T) xs[fb_skew(L)] = 0;
@@ -857,10 +862,10 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         if (max_order > 4) max_order = 4;
         int opt = min_order;
         uint32_t best = 0xffffffffu;
-        for (int base = min_order; base <= max_order; base += FB_GROUP) {
+        for (int base = min_order; base <= max_order; base += FB_GROUP_OF(MAXP)) {
             int cnt = 0;
             ord = 0;
-            for (int i = base; i <= max_order && cnt < FB_GROUP; i++) ord = fb_order_put(ord, cnt++, i);
+            for (int i = base; i <= max_order && cnt < FB_GROUP_OF(MAXP); i++) ord = fb_order_put(ord, cnt++, i);
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             int bs = -1;
             for (int s = 0; s < cnt; s++) {
@@ -895,10 +900,10 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         /* optimize.c:205-222: `levels` fixed orders, highest first */
         const int levels = 1 << (om - 1);
         opt_order = max_order - 1;
-        for (int base = levels - 1; base >= 0; base -= FB_GROUP) {
+        for (int base = levels - 1; base >= 0; base -= FB_GROUP_OF(MAXP)) {
             int cnt = 0;
             ord = 0;
-            for (int i = base; i >= 0 && cnt < FB_GROUP; i--) {
+            for (int i = base; i >= 0 && cnt < FB_GROUP_OF(MAXP); i--) {
                 int order = min_order + (((max_order - min_order + 1) * (i + 1)) / levels) - 2;
                 if (order < 0) order = 0;
                 ord = fb_order_put(ord, cnt, order + 1); cnt++;
@@ -914,10 +919,10 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     } else if (om == 5) {
         /* optimize.c:223-240: every order */
         opt_order = 0;
-        for (int base = 0; base < max_order; base += FB_GROUP) {
+        for (int base = 0; base < max_order; base += FB_GROUP_OF(MAXP)) {
             int cnt = 0;
             ord = 0;
-            for (int i = base; i < max_order && cnt < FB_GROUP; i++) ord = fb_order_put(ord, cnt++, i + 1);
+            for (int i = base; i < max_order && cnt < FB_GROUP_OF(MAXP); i++) ord = fb_order_put(ord, cnt++, i + 1);
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             int bs = -1;
             for (int s = 0; s < cnt; s++) {
@@ -952,7 +957,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 cm &= range & ~(done | gmask);
                 const uint32_t cor = __reduce_or_sync(FB_FULL_MASK, live ? cm : 0u);
                 const uint32_t cand = __reduce_and_sync(FB_FULL_MASK, live ? cm : 0xffffffffu);
-                if (cor != cand || cnt + __popc(cor) > FB_GROUP) break;
+                if (cor != cand || cnt + __popc(cor) > FB_GROUP_OF(MAXP)) break;
                 for (uint32_t m = cor; m; m &= m - 1) { ord = fb_order_put(ord, cnt, __ffs((int)m)); cnt++; }
                 gmask |= cor; hyp |= cor; nsteps++;
             }
@@ -964,7 +969,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 for (int i = last - step; i <= last + step; i += step) {
                     if (i < lo || i > hi || ((done >> i) & 1u)) continue;
                     int s = 0;
-                    for (int q = 1; q < FB_GROUP; q++) if (q < cnt && fb_order_of(ord, q) == i + 1) s = q;
+                    for (int q = 1; q < FB_GROUP_OF(MAXP); q++) if (q < cnt && fb_order_of(ord, q) == i + 1) s = q;
                     const uint32_t b = S.result[s];
                     done |= 1u << i;
                     if (b < best) { best = b; opt_order = i; bs = s; }

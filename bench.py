@@ -254,6 +254,11 @@ def workload_config(n_gpus):
 # GPU arm
 # --------------------------------------------------------------------------
 def run_gpu_arm(args):
+    # stdout carries exactly one JSON line: whatever native libraries print there (NCCL's
+    # "NCCL version ..." banner under torchrun) is sent to stderr; the line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from flake_b200 import api
@@ -519,7 +524,7 @@ def run_gpu_arm(args):
         "compression_ratio": round(out_bytes / float(nsamples * CHANNELS * 2), 4),
         "step_ms": [round(x, 2) for x in step_ms],
     }
-    print(json.dumps(line), flush=True)
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     enc.close()
     if world > 1:
         dist.destroy_process_group()

@@ -29,7 +29,7 @@
 
 #define FB_MAX_ORDER 32
 #ifndef FB_LPC_WARPS
-#define FB_LPC_WARPS 2                                  /* warps per CTA */
+#define FB_LPC_WARPS 1                                  /* warps per CTA: 17 resident warps per SM at 118 registers (2: 16) */
 #endif
 #define FB_LPC_THREADS (32 * FB_LPC_WARPS)
 #define FB_LPC_SUBS_PER_CTA (16 * FB_LPC_WARPS)         /* a warp owns 16 subframes */

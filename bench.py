@@ -10,20 +10,32 @@ stereo 44.1 kHz stream = 158,760,000 inter-channel samples, 38,760 blocks of 409
 A *step* is one pass of the hot path over that whole stream on every rank (each
 rank encodes its own stream: frames shard with no collective, weak scaling).
 
-  value  MSamples/s with the PCM already resident in HBM (packed s16le, the WAV
-         data layout), device-resident outputs, CUDA events on the launching
-         stream, max over ranks.
-  e2e    the same metric through the host-buffer C ABI (flake_b200_encode_stream
-         on int32 samples -- the flake_encode_frame convention): H2D, kernels,
-         D2H and the MD5 of the PCM all inside the timed region.
+  value   MSamples/s, KERNELS ONLY: PCM already resident in HBM (packed s16le, the
+          WAV data layout), device-resident outputs, CUDA events on the launching
+          stream, max over ranks.  No H2D/D2H, no MD5.
+  e2e     the like-for-like figure against the reference arm: the same metric through
+          the host-buffer C ABI (flake_b200_encode_stream on int32 samples -- the
+          flake_encode_frame convention): H2D, kernels, D2H, the MD5 of the PCM and the
+          final STREAMINFO all inside the timed region.
+  parity  the e2e output byte-compared with the compiled reference over the WHOLE
+          stream: frames compared / mismatching, compressed size delta.
+  other_configs  C1 / C3 / C4 of BASELINE.json: device-resident rate, stage times,
+          roofline of their dominant kernel, parity against the reference.
+  e2e_corpus     a FIXED corpus of 1 h streams through flake_b200_encode_corpus (one
+          process drives every GPU it is given): strong scaling over --gpus.
+
+All arms and the full-size parity tests draw their PCM from ONE generator
+(flake_b200.synth.long_pcm, CPU, deterministic).
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref
-compiled from the reference sources, else the oracle port) on the host cores.
+compiled from the reference sources and driven from C by oracle/ref_shim.c, else
+the oracle port) on the host cores.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -36,9 +48,24 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-C2_SAMPLES = 158_760_000          # 1 h at 44.1 kHz
-RATE, CHANNELS, BPS, LEVEL, BLOCK = 44100, 2, 16, 8, 4096
 HBM_FALLBACK_GBS = 6650.0         # B200_PROFILING.md fallback
+
+CONFIGS = {
+    # name: level, channels, bits, rate, samples, block (SURVEY.md section 8 shorthand)
+    "C1": dict(level=5, ch=2, bps=16, rate=44100, samples=26_460_000, block=4096,
+               what="flake -5 (LPC<=8, order estimate), 10 min 16-bit stereo 44.1 kHz"),
+    "C2": dict(level=8, ch=2, bps=16, rate=44100, samples=158_760_000, block=4096,
+               what="flake -8 (LPC<=12 log search, Rice partition order 0..6, mid/side estimate), "
+                    "1 h 16-bit stereo 44.1 kHz"),
+    "C3": dict(level=12, ch=2, bps=24, rate=96000, samples=57_600_000, block=8192,
+               what="flake -12 (LPC<=32 exhaustive order search, partition order 0..8, VBS), "
+                    "10 min 24-bit stereo 96 kHz"),
+    "C4": dict(level=9, ch=8, bps=24, rate=48000, samples=28_800_000, block=4096,
+               what="flake -9 (LPC<=12 log search, partition order 0..8, VBS), 10 min 8-channel 24-bit 48 kHz"),
+}
+C2 = CONFIGS["C2"]
+RATE, CHANNELS, BPS, LEVEL, BLOCK = C2["rate"], C2["ch"], C2["bps"], C2["level"], C2["block"]
+C2_SAMPLES = C2["samples"]
 
 
 def env_int(name, default):
@@ -48,58 +75,22 @@ def env_int(name, default):
         return default
 
 
-# --------------------------------------------------------------------------
-# synthetic PCM of the C2 shape, generated on the device (fast, deterministic)
-# --------------------------------------------------------------------------
-def synth_device(nsamples: int, seed: int, device):
-    """(nsamples, 2) int16 on `device`: sines + chirp under an envelope, shaped
-    noise bursts, a white floor, sparse impulses, silence / DC / quiet stretches
-    (the recipe of flake_b200/synth.py)."""
-    import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(0xF1A4E000 + seed)
-    out = torch.empty((nsamples, 2), dtype=torch.int16, device=device)
-    seg = 1 << 22
-    full = 32767.0
-    rs = np.random.RandomState(seed + 12345)
-    freqs = rs.uniform(60.0, 5000.0, size=5)
-    amps = rs.uniform(0.03, 0.22, size=5)
-    phases = rs.uniform(0, 2 * np.pi, size=5)
-    env_f = rs.uniform(0.05, 0.4)
-    shift = int(rs.randint(1, 40))
-    prev_tail = None
-    for s0 in range(0, nsamples, seg):
-        n = min(seg, nsamples - s0)
-        t = (torch.arange(s0, s0 + n, device=device, dtype=torch.float64) / RATE)
-        x = torch.zeros(n, dtype=torch.float64, device=device)
-        for k in range(5):
-            if k == 0:
-                ph = 2 * np.pi * (freqs[0] * t + 0.5 * (freqs[0] * 0.8) * t * t / 3600.0)
-            else:
-                ph = 2 * np.pi * freqs[k] * t
-            x += amps[k] * torch.sin(ph + phases[k])
-        x *= (0.55 + 0.45 * torch.sin(2 * np.pi * env_f * t)) * full
-        noise = torch.randn(n, generator=g, device=device, dtype=torch.float32).double()
-        lp = noise.clone()
-        lp[1:] = 0.5 * noise[1:] + 0.5 * noise[:-1]
-        lp[2:] = 0.5 * lp[2:] + 0.5 * lp[:-2]
-        burst = ((torch.arange(s0, s0 + n, device=device) // 4096) % 9 == 0).double()
-        x += burst * 0.03 * full * lp + 0.003 * full * noise
-        imp = (torch.rand(n, generator=g, device=device) < 1.0 / 20000.0).double()
-        x += imp * (torch.rand(n, generator=g, device=device).double() - 0.5) * 1.2 * full
-        left = x
-        # right: delayed, attenuated copy + independent noise
-        src = torch.cat([prev_tail if prev_tail is not None else left[:shift] * 0, left])
-        right = 0.8 * src[:n] + 0.02 * full * torch.randn(n, generator=g, device=device).double()
-        prev_tail = left[-shift:].clone()
-        blk = torch.stack([left, right], dim=1)
-        # stretches of silence / DC / low level, a few seconds each, every ~3 min
-        pos = (torch.arange(s0, s0 + n, device=device) % (RATE * 180))
-        blk[(pos < RATE * 2)] = 0.0
-        blk[(pos >= RATE * 60) & (pos < RATE * 62)] = round(0.1 * full)
-        blk[(pos >= RATE * 120) & (pos < RATE * 123)] *= 0.05
-        out[s0:s0 + n] = torch.clamp(torch.round(blk), -32768, 32767).to(torch.int16)
-    return out
+def workload_pcm(cfg, seed, nsamples=None):
+    """int32 (n, ch) PCM of a BASELINE.json configuration: the one generator of every arm."""
+    from flake_b200 import synth
+    return synth.long_pcm(nsamples or cfg["samples"], cfg["ch"], cfg["bps"], cfg["rate"], seed=seed)
+
+
+def csrc_fingerprint():
+    """sha1 over the kernel sources: profiles/traffic.json is only quoted for the kernels it
+    was captured from."""
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "flake_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 # --------------------------------------------------------------------------
@@ -157,36 +148,79 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # CPU legs (the only places bench.py touches oracle/)
 # --------------------------------------------------------------------------
-def cpu_encode_threads(pcm_i32: np.ndarray, threads: int, steps: int, warmup: int):
-    """Encode `threads` contiguous segments of pcm_i32 concurrently, one reference
-    context per thread (the reference API is single-threaded per context).
-    Returns (best MSamples/s, list of step seconds, kind)."""
+def cpu_reference_time(pcm_i32: np.ndarray, cfg, threads: int, steps: int, warmup: int):
+    """Time the reference over pcm_i32: `threads` contiguous block ranges, one reference
+    context and one thread each, every block through flake_encode_frame in a C loop
+    (oracle/ref_shim.c; no per-block Python).  Returns (samples, [seconds], kind, bytes)."""
     from oracle import pyoracle as po
-    from flake_b200 import api
     n = pcm_i32.shape[0]
-    seg = (n // threads) // BLOCK * BLOCK
-    kind = "reference" if po.have_ref() else "port"
-    ref = po.ref_library() if kind == "reference" else None
+    times, nbytes = [], 0
+    if po.have_ref():
+        kind = "reference"
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            out, _, _ = po.ref_encode_parallel(pcm_i32, cfg["rate"], cfg["bps"], cfg["level"], threads=threads)
+            dt = time.perf_counter() - t0
+            nbytes = len(out)
+            if it >= warmup:
+                times.append(dt)
+    else:
+        kind = "port"
+        seg = (n // threads) // cfg["block"] * cfg["block"]
+        res = [0] * threads
 
-    def work(t):
-        part = pcm_i32[t * seg:(t + 1) * seg]
-        if ref is not None:
-            api.encode_per_block(ref, part, RATE, BPS, LEVEL)
-        else:
-            po.encode_stream(part, RATE, BPS, LEVEL)
+        def work(t):
+            res[t] = len(po.encode_stream(pcm_i32[t * seg:(t + 1) * seg], cfg["rate"], cfg["bps"], cfg["level"])[0])
+        for it in range(warmup + steps):
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+            t0 = time.perf_counter()
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            dt = time.perf_counter() - t0
+            nbytes = sum(res)
+            if it >= warmup:
+                times.append(dt)
+        n = seg * threads
+    return n, times, kind, nbytes
 
-    times = []
-    for it in range(warmup + steps):
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-        t0 = time.perf_counter()
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    return seg * threads, times, kind
+
+def reference_bytes(pcm_i32: np.ndarray, cfg):
+    """(frame bytes, bytes per block) of the whole stream from the reference on all host
+    cores (untimed; the checker of the parity legs)."""
+    from oracle import pyoracle as po
+    if po.have_ref():
+        out, per_block, _ = po.ref_encode_parallel(pcm_i32, cfg["rate"], cfg["bps"], cfg["level"], threads=0)
+        return out, per_block.astype(np.int64), "reference"
+    data, flen, fbs, _ = po.encode_stream(pcm_i32, cfg["rate"], cfg["bps"], cfg["level"])
+    # the port reports frames; fold them into blocks
+    blk = (np.cumsum(fbs) - fbs) // cfg["block"]
+    per_block = np.bincount(blk, weights=flen).astype(np.int64)
+    return np.frombuffer(data, dtype=np.uint8), per_block, "port"
+
+
+def parity_record(got: np.ndarray, flen: np.ndarray, fbs: np.ndarray, want: np.ndarray, per_block: np.ndarray, cfg, kind):
+    """Frames compared / mismatching against the reference's bytes, size delta in percent."""
+    nframes = int(len(flen))
+    rec = {"frames_compared": nframes, "frames_mismatching": 0,
+           "size_delta_pct": round(100.0 * (len(got) - len(want)) / max(1, len(want)), 6),
+           "bytes": int(len(got)), "reference_bytes": int(len(want)), "against": kind,
+           "scope": "whole stream, every frame byte"}
+    if len(got) == len(want) and np.array_equal(got, want):
+        return rec
+    blk = (np.cumsum(fbs) - fbs) // cfg["block"]
+    mine = np.bincount(blk, weights=flen, minlength=len(per_block)).astype(np.int64)
+    mo = np.concatenate([[0], np.cumsum(mine)])
+    ro = np.concatenate([[0], np.cumsum(per_block)])
+    fpb = np.bincount(blk, minlength=len(per_block))
+    bad = 0
+    for b in range(min(len(mine), len(per_block))):
+        x, y = got[mo[b]:mo[b + 1]], want[ro[b]:ro[b + 1]]
+        if len(x) != len(y) or not np.array_equal(x, y):
+            bad += int(fpb[b])
+    rec["frames_mismatching"] = bad + abs(len(mine) - len(per_block))
+    return rec
 
 
 def run_reference_arm(args):
@@ -196,36 +230,30 @@ def run_reference_arm(args):
     and its API is serial per stream (frame numbers and the MD5 chain through every block), so
     the most host threads the reference can use on this workload is one per stream:
     `--gpus N` streams -> N threads, one FlakeContext each.  Each step encodes a bounded sample
-    (the first ~66 s of audio) of every stream.  For orientation the line also carries
-    `all_cores`: every host core busy, each on its own independent stream segment -- more
-    streams than the workload has, i.e. what a corpus of many files would reach.
+    (the first ~4.4 min of audio) of the GPU arm's own stream (same generator, same seed).  For
+    orientation the line also carries `all_cores`: every host core busy, each on its own block
+    range -- more parallelism than the API offers one stream, i.e. what a corpus of many files
+    would reach.
     """
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    from flake_b200 import synth
     cores = os.cpu_count() or 1
     streams = max(1, min(args.gpus, cores))
     threads = env_int("FLAKE_BENCH_REF_THREADS", streams)
     per_thread = env_int("FLAKE_BENCH_REF_SAMPLES_PER_THREAD", BLOCK * 2800)   # 11.5 M samples, ~1 s of CPU
-    base = synth.synth_pcm(BLOCK * 700, CHANNELS, BPS, RATE, seed=0)
-
-    def tiled(total):
-        reps = (total + base.shape[0] - 1) // base.shape[0]
-        return np.ascontiguousarray(np.tile(base, (reps, 1))[:total])
-
-    pcm = tiled(per_thread * threads)
-    total, times, kind = cpu_encode_threads(pcm, threads, args.steps, max(1, min(args.warmup, 1)))
+    pcm = workload_pcm(C2, 0, per_thread * threads)
+    total, times, kind, _ = cpu_reference_time(pcm, C2, threads, args.steps, max(1, min(args.warmup, 1)))
     ms = 1e3 * float(np.mean(times))
     val = total / (ms * 1e-3) / 1e6
-    sample = "%d stream(s) x first %d samples (%.0f s of audio) per step, one thread per stream" % (
-        threads, total // threads, total / threads / RATE)
+    sample = "%d block range(s) x %d samples (%.0f s of audio) of the GPU arm's rank-0 stream per step, " \
+             "one thread + one reference context per range, C loop over flake_encode_frame" % (
+                 threads, total // threads, total / threads / RATE)
     allc = None
     if cores > threads and not os.environ.get("FLAKE_BENCH_SKIP_ALL_CORES"):
-        seg = BLOCK * 700
-        t2, times2, _ = cpu_encode_threads(tiled(seg * cores), cores, 1, 1)
+        t2, times2, _, _ = cpu_reference_time(workload_pcm(C2, 0, BLOCK * 700 * cores), C2, cores, 1, 1)
         allc = {"value": round(t2 / times2[0] / 1e6, 3), "unit": "MSamples/s", "cores": cores,
-                "sample": "%d independent stream segments of %d samples" % (cores, seg)}
+                "sample": "%d block ranges of %d samples" % (cores, t2 // cores)}
     line = {
         "impl": "reference", "metric": "MSamples/s encoded, flake -8", "value": round(val, 3),
         "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -242,12 +270,130 @@ def run_reference_arm(args):
 
 
 def workload_config(n_gpus):
-    return {"workload": "C2: flake -8 (LPC<=12 log search, Rice partition order 0..6, mid/side estimate), "
-                        "1 h 16-bit stereo 44.1 kHz = 158760000 samples, 38760 blocks of 4096, per GPU",
+    return {"workload": "C2: " + C2["what"] + " = 158760000 samples, 38760 blocks of 4096, per GPU",
             "level": LEVEL, "block_size": BLOCK, "channels": CHANNELS, "bits_per_sample": BPS,
             "sample_rate": RATE, "samples_per_gpu": C2_SAMPLES,
+            "generator": "flake_b200.synth.long_pcm(seed = rank), the same in both arms",
             "l2": "inputs (635 MB packed PCM per pass) larger than the 126 MB L2; no explicit flush",
             "sharding": "one stream per rank, no collective" if n_gpus > 1 else "single stream"}
+
+
+# --------------------------------------------------------------------------
+# GPU arm helpers
+# --------------------------------------------------------------------------
+def to_device_packed(pcm_i32: np.ndarray, cfg, dev):
+    """The WAV data-chunk layout in HBM: packed little-endian, ceil(bps/8) bytes per sample."""
+    import torch
+    from flake_b200 import api, synth
+    if cfg["bps"] == 16:
+        return torch.from_numpy(pcm_i32.astype(np.int16)).to(dev), api.PCM_S16LE
+    if cfg["bps"] == 24:
+        raw = np.frombuffer(synth.pack_pcm(pcm_i32, 24), dtype=np.uint8)
+        return torch.from_numpy(raw.copy()).to(dev), api.PCM_S24LE
+    return torch.from_numpy(pcm_i32).to(dev), api.PCM_S32
+
+
+class DevicePass:
+    """One configuration resident in HBM: the device-only pass, its timing and roofline."""
+
+    def __init__(self, lib, cfg, pcm_i32, dev, stream):
+        import torch
+        from flake_b200 import api
+        self.lib, self.cfg, self.dev, self.stream = lib, cfg, dev, stream
+        self.n = pcm_i32.shape[0]
+        self.enc = api.Encoder(lib, cfg["ch"], cfg["rate"], cfg["bps"], self.n, cfg["level"])
+        self.enc.init()
+        self.ctx = C.byref(self.enc.ctx)
+        self.d_pcm, self.fmt = to_device_packed(pcm_i32, cfg, dev)
+        self.bytes_per_sample = cfg["ch"] * ((cfg["bps"] + 7) // 8)
+        cap_s, cap_b, cap_f = C.c_ulonglong(), C.c_ulonglong(), C.c_uint()
+        assert lib.flake_b200_device_capacity(self.ctx, C.byref(cap_s), C.byref(cap_b), C.byref(cap_f)) == 0
+        self.chunk = int(cap_s.value)
+        self.nchunks = (self.n + self.chunk - 1) // self.chunk
+        self.d_out = torch.empty(int(cap_b.value), dtype=torch.uint8, device=dev)
+        self.d_flen = torch.empty(int(cap_f.value), dtype=torch.int32, device=dev)
+        self.d_sum = torch.zeros((self.nchunks, 3), dtype=torch.int64, device=dev)   # 24-byte FbSummary per chunk
+        self.base = self.d_pcm.data_ptr()
+
+    def run(self):
+        allow_vbs = bool(self.enc.ctx.params.allow_vbs)
+        for k in range(self.nchunks):
+            s0 = k * self.chunk
+            ns = min(self.chunk, self.n - s0)
+            first = s0 if allow_vbs else s0 // self.cfg["block"]
+            rc = self.lib.flake_b200_encode_device(
+                self.ctx, self.base + s0 * self.bytes_per_sample, self.fmt, ns, first, self.d_out.data_ptr(),
+                self.d_flen.data_ptr(), None, self.d_sum[k].data_ptr(), self.stream.cuda_stream)
+            if rc:
+                raise RuntimeError("flake_b200_encode_device failed: %d" % rc)
+
+    def totals(self):
+        summ = self.d_sum.cpu().numpy().view(np.uint8).reshape(self.nchunks, 24)
+        frames = int(sum(int(np.frombuffer(summ[k, 0:4].tobytes(), np.uint32)[0]) for k in range(self.nchunks)))
+        out_bytes = int(sum(int(np.frombuffer(summ[k, 8:16].tobytes(), np.uint64)[0]) for k in range(self.nchunks)))
+        return frames, out_bytes
+
+    def stage_profile(self, passes):
+        import torch
+        self.enc.set_profiling(True)
+        for _ in range(passes):
+            self.run()
+        torch.cuda.synchronize()
+        stages = self.enc.stage_times()
+        self.enc.set_profiling(False)
+        return stages
+
+    def close(self):
+        self.enc.close()
+
+
+def roofline_record(stages, passes, nsamples, nchunks, in_bytes_per_sample, out_bytes, peak_gbs, peak_src, traffic):
+    stage_ms = {k: v[0] for k, v in stages.items()}
+    stage_n = {k: v[1] for k, v in stages.items()}
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    dom_avg_ms = stage_ms[dom] / max(1, stage_n[dom])
+    # algorithmic bytes per launch (SURVEY.md 8d): packed PCM in + FLAC frame bytes out,
+    # for the samples one launch (= one chunk) processes
+    algo_bytes = (in_bytes_per_sample + out_bytes / float(nsamples)) * nsamples / float(nchunks)
+    achieved = algo_bytes / (dom_avg_ms * 1e-3) / 1e9
+    step_ms = sum(stage_ms.values()) / passes
+    rec = {"bound": "hbm", "kernel": "k_" + dom, "achieved": round(achieved, 2), "peak": peak_gbs,
+           "unit": "GB/s", "frac": round(achieved / peak_gbs, 5),
+           "traffic": (traffic or {}).get(dom) if traffic else None,
+           "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
+           "kernel_ms_per_launch": round(dom_avg_ms, 4),
+           "whole_step_frac": round(algo_bytes * nchunks / (step_ms * 1e-3) / 1e9 / peak_gbs, 5),
+           "stage_ms_per_step": {k: round(v / passes, 3) for k, v in stage_ms.items()},
+           "stage_share": {k: round(v / max(1e-9, sum(stage_ms.values())), 4) for k, v in stage_ms.items()},
+           "note": "path is instruction-bound (integer/FP64 pipes), not HBM-bound; see DESIGN.md 6"}
+    if traffic:
+        rec["traffic_all_kernels"] = {k: traffic.get(k) for k in stage_ms if traffic.get(k) is not None}
+    return rec
+
+
+def host_encode(lib, cfg, pcm_i32):
+    """Whole stream through the host-buffer C ABI (int32 in, frames + lengths out)."""
+    from flake_b200 import api
+    enc = api.Encoder(lib, cfg["ch"], cfg["rate"], cfg["bps"], pcm_i32.shape[0], cfg["level"])
+    enc.init()
+    try:
+        data, flen, fbs = enc.encode_stream(pcm_i32, api.PCM_S32, pcm_i32.shape[0])
+    finally:
+        enc.close()
+    return data, flen, fbs
+
+
+def load_traffic():
+    """profiles/traffic.json (ncu dram bytes per launch) -- only if it was captured from the
+    kernel sources of this tree."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+    except Exception:
+        return None, "profiles/traffic.json missing"
+    if t.get("csrc_sha1_16") != csrc_fingerprint():
+        return None, "profiles/traffic.json is from other kernel sources (%s): not quoted" % t.get("csrc_sha1_16")
+    return t, t.get("source")
 
 
 # --------------------------------------------------------------------------
@@ -269,41 +415,15 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; flake_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")     # host-side waits that must not occupy SMs
 
     nsamples = env_int("FLAKE_BENCH_SAMPLES", C2_SAMPLES)
     lib = api.load_library()
     lib.flake_b200_set_device(local)
-    enc = api.Encoder(lib, CHANNELS, RATE, BPS, nsamples, LEVEL)
-    enc.init()
-    ctx = C.byref(enc.ctx)
-
-    # ---- inputs -------------------------------------------------------------
-    d_pcm = synth_device(nsamples, seed=rank, device=dev)              # packed s16le in HBM
-    cap_s, cap_b, cap_f = C.c_ulonglong(), C.c_ulonglong(), C.c_uint()
-    assert lib.flake_b200_device_capacity(ctx, C.byref(cap_s), C.byref(cap_b), C.byref(cap_f)) == 0
-    chunk = int(cap_s.value)
-    nchunks = (nsamples + chunk - 1) // chunk
-    d_out = torch.empty(int(cap_b.value), dtype=torch.uint8, device=dev)
-    d_flen = torch.empty(int(cap_f.value), dtype=torch.int32, device=dev)
-    d_sum = torch.zeros((nchunks, 3), dtype=torch.int64, device=dev)   # 24-byte FbSummary per chunk
-    # a real (non-default) torch stream: the library treats a NULL handle as "use the
-    # context's own stream", and torch events must see the stream the kernels run on
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-
-    def device_pass():
-        for k in range(nchunks):
-            s0 = k * chunk
-            ns = min(chunk, nsamples - s0)
-            rc = lib.flake_b200_encode_device(
-                ctx, d_pcm[s0:].data_ptr(), api.PCM_S16LE, ns, s0 // BLOCK, d_out.data_ptr(),
-                d_flen.data_ptr(), None, d_sum[k].data_ptr(), stream.cuda_stream)
-            if rc:
-                raise RuntimeError("flake_b200_encode_device failed: %d" % rc)
 
     def barrier():
         torch.cuda.synchronize()
@@ -311,11 +431,27 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # a real (non-default) torch stream: the library treats a NULL handle as "use the
+    # context's own stream", and torch events must see the stream the kernels run on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+
+    # ---- inputs: rank r encodes stream r of the corpus ------------------------------
+    pcm_np = workload_pcm(C2, rank, nsamples)
+    dp = DevicePass(lib, C2, pcm_np, dev, stream)
+
     # ---- device-resident timing ------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        device_pass()
+        dp.run()
     barrier()
-    st0 = enc.stats()
+    st0 = dp.enc.stats()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -323,43 +459,36 @@ def run_gpu_arm(args):
     barrier()
     ev[0].record(stream)
     for i in range(args.steps):
-        device_pass()
+        dp.run()
         ev[i + 1].record(stream)
     barrier()
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[args.steps])
-    st1 = enc.stats()
+    st1 = dp.enc.stats()
     launches = int(st1.kernel_launches - st0.kernel_launches)
     # per-kernel CUDA events (on the launching stream) in passes of their own, so that the
     # event records do not sit inside the timed region above
     prof_passes = max(1, min(args.steps, 5))
-    enc.set_profiling(True)
-    for _ in range(prof_passes):
-        device_pass()
-    torch.cuda.synchronize()
-    stages = enc.stage_times()
-    enc.set_profiling(False)
-    summ = d_sum.cpu().numpy().view(np.uint8).reshape(nchunks, 24)
-    frames = int(sum(int(np.frombuffer(summ[k, 0:4].tobytes(), np.uint32)[0]) for k in range(nchunks)))
-    out_bytes = int(sum(int(np.frombuffer(summ[k, 8:16].tobytes(), np.uint64)[0]) for k in range(nchunks)))
-
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    ms_per_step = total_ms_max / args.steps
+    stages = dp.stage_profile(prof_passes)
+    frames, out_bytes = dp.totals()
+    ms_per_step = allmax(total_ms) / args.steps
     value = world * nsamples / (ms_per_step * 1e-3) / 1e6
+    rank_ms = None
+    if world > 1:
+        g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([total_ms / args.steps], dtype=torch.float64, device=dev))
+        rank_ms = [round(float(x.item()), 3) for x in g]
 
     # ---- end-to-end through the host-buffer C ABI -----------------------------------
     e2e_steps = max(1, min(args.steps, env_int("FLAKE_BENCH_E2E_STEPS", 3)))
-    h_pcm32 = torch.empty((nsamples, CHANNELS), dtype=torch.int32, pin_memory=True)
-    h_pcm32.copy_(d_pcm.to(torch.int32))
-    torch.cuda.synchronize()
-    pcm_np = h_pcm32.numpy()
-    cap = int(lib.flake_b200_max_encoded_size(ctx, nsamples))
+    h_pcm32 = torch.from_numpy(pcm_np).pin_memory()
+    pcm_pinned = h_pcm32.numpy()
+    ctx0 = C.byref(dp.enc.ctx)
+    cap = int(lib.flake_b200_max_encoded_size(ctx0, nsamples))
     h_out = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
     nblocks = (nsamples + BLOCK - 1) // BLOCK
     h_flen = np.zeros(nblocks + 1, dtype=np.uint32)
+    h_fbs = np.zeros(nblocks + 1, dtype=np.uint32)
     nf = C.c_uint(0)
     e2e_ms, e2e_bytes, md5_hex = [], 0, None
     h2d = d2h = 0
@@ -369,8 +498,8 @@ def run_gpu_arm(args):
         lib.flake_b200_reset_stream(C.byref(enc2.ctx))
         barrier()
         t0 = time.perf_counter()
-        rc = lib.flake_b200_encode_stream(C.byref(enc2.ctx), pcm_np.ctypes.data, api.PCM_S32, nsamples,
-                                          h_out.data_ptr(), cap, h_flen.ctypes.data, None,
+        rc = lib.flake_b200_encode_stream(C.byref(enc2.ctx), pcm_pinned.ctypes.data, api.PCM_S32, nsamples,
+                                          h_out.data_ptr(), cap, h_flen.ctypes.data, h_fbs.ctypes.data,
                                           nblocks + 1, C.byref(nf))
         si, si_bytes = enc2.streaminfo()          # final STREAMINFO incl. MD5: the stream is complete
         dt = time.perf_counter() - t0
@@ -381,83 +510,29 @@ def run_gpu_arm(args):
             e2e_ms.append(dt * 1e3)
             e2e_bytes, h2d, d2h = int(rc), int(st.h2d_bytes), int(st.d2h_bytes)
             md5_hex = bytes(si.md5sum).hex()
+    e2e_stats = enc2.stats()
     enc2.close()
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t.item())
+    e2e_ms_max = allmax(float(np.mean(e2e_ms)))
     e2e_value = world * nsamples / (e2e_ms_max * 1e-3) / 1e6
 
-    # ---- corpus shape (C5): several independent streams through one GPU at once ----------
-    # Each stream has its own context, lanes and MD5 thread; the single-stream figure above is
-    # bound by the serial MD5 chain of its one stream, this one shows what the device sustains.
-    multi = None
-    # one MD5 thread per stream is what saturates a host core (the caller threads mostly wait): measured on
-    # a 16-core box, 8 / 12 / 15 streams -> 1435 / 1838 / 2148 MSamples/s
-    nstreams = env_int("FLAKE_BENCH_STREAMS", max(1, min(15, ((os.cpu_count() or 2) - 1) // max(1, world))))
-    if nstreams > 1 and not os.environ.get("FLAKE_BENCH_SKIP_MULTI"):
-        # no collective inside the try: a rank that fails must still reach the reductions below
-        best, same, why = float("nan"), False, None
-        encs = []
+    # ---- corpus shape (C5) through the C corpus entry point: strong scaling -------------
+    corpus = None
+    if rank == 0 and not os.environ.get("FLAKE_BENCH_SKIP_CORPUS") and hasattr(lib, "flake_b200_encode_corpus"):
         try:
-            outs, flens = [], []
-            for _ in range(nstreams):
-                e = api.Encoder(lib, CHANNELS, RATE, BPS, nsamples, LEVEL)
-                e.init()
-                encs.append(e)
-                outs.append(torch.empty(cap, dtype=torch.uint8, pin_memory=True))
-                flens.append(np.zeros(nblocks + 1, dtype=np.uint32))
-            rcs = [0] * nstreams
-
-            def one(i):
-                n_out = C.c_uint(0)
-                lib.flake_b200_reset_stream(C.byref(encs[i].ctx))
-                rcs[i] = lib.flake_b200_encode_stream(C.byref(encs[i].ctx), pcm_np.ctypes.data, api.PCM_S32, nsamples,
-                                                      outs[i].data_ptr(), cap, flens[i].ctypes.data, None,
-                                                      nblocks + 1, C.byref(n_out))
-                encs[i].streaminfo()
-
-            for it in range(2):
-                ths = [threading.Thread(target=one, args=(i,)) for i in range(nstreams)]
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for th in ths:
-                    th.start()
-                for th in ths:
-                    th.join()
-                dt = time.perf_counter() - t0
-                if min(rcs) < 0:
-                    raise RuntimeError("flake_b200_encode_stream failed: %s" % rcs)
-                if it >= 1:
-                    best = dt
-            same = bytes(outs[1][:int(rcs[1])].numpy().tobytes()) == bytes(outs[0][:int(rcs[0])].numpy().tobytes())
-            del outs
+            corpus = run_corpus_leg(lib, api, pcm_pinned, nsamples, world, torch)
         except Exception as exc:            # informative only
-            why = str(exc)[:200]
-        for e in encs:
-            try:
-                e.close()
-            except Exception:
-                pass
-        t = torch.tensor([best if best == best else 1e30], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if float(t.item()) < 1e29:
-            multi = {"value": round(world * nstreams * nsamples / float(t.item()) / 1e6, 2), "unit": "MSamples/s",
-                     "streams_per_gpu": nstreams, "ms": round(float(t.item()) * 1e3, 1), "outputs_identical": bool(same),
-                     "note": "independent 1 h streams encoded concurrently through the host-buffer C ABI, "
-                             "one context + MD5 thread each (the C5 corpus shape); ranks not barrier-aligned"}
-        else:
-            multi = {"value": None, "error": why or "failed on another rank"}
+            corpus = {"value": None, "error": str(exc)[:300]}
+    if world > 1:
+        dist.barrier(group=host_group)      # the other ranks wait on the host: rank 0 used their GPUs
 
     if rank != 0:
-        enc.close()
+        dp.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (CUDA events between kernels, timed region) ---
+    # ---- roofline of the dominant kernel (CUDA events between kernels) ---------------
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -466,45 +541,49 @@ def run_gpu_arm(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    stage_ms = {k: v[0] for k, v in stages.items()}
-    stage_n = {k: v[1] for k, v in stages.items()}
-    dom = max(stage_ms, key=lambda k: stage_ms[k])
-    dom_avg_ms = stage_ms[dom] / max(1, stage_n[dom])
-    # algorithmic bytes per launch: packed PCM in + FLAC frame bytes out,
-    # for the samples one launch (= one chunk) processes
-    bytes_per_sample = CHANNELS * 2 + out_bytes / float(nsamples)
-    samples_per_launch = nsamples / float(nchunks)
-    algo_bytes = bytes_per_sample * samples_per_launch
-    achieved = algo_bytes / (dom_avg_ms * 1e-3) / 1e9
-    ncu_traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            ncu_traffic = json.load(f).get(dom)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": round(achieved, 2), "peak": peak_gbs,
-                "unit": "GB/s", "frac": round(achieved / peak_gbs, 5), "traffic": ncu_traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
-                "kernel_ms_per_launch": round(dom_avg_ms, 4),
-                "stage_ms_per_step": {k: round(v / prof_passes, 3) for k, v in stage_ms.items()},
-                "stage_share": {k: round(v / max(1e-9, sum(stage_ms.values())), 4) for k, v in stage_ms.items()},
-                "note": "path is instruction-bound (integer/FP64 pipes), not HBM-bound; see DESIGN.md 6"}
+    traffic, traffic_src = load_traffic()
+    roofline = roofline_record(stages, prof_passes, nsamples, dp.nchunks, CHANNELS * 2, out_bytes, peak_gbs, peak_src,
+                               (traffic or {}).get("C2") if traffic else None)
+    roofline["traffic_source"] = traffic_src
 
-    # ---- CPU baseline: the compiled reference on one host core, bounded sample --------
+    # ---- parity of the e2e output against the reference, whole stream (untimed) ----------
+    parity = None
     cpu = None
     try:
-        budget = env_int("FLAKE_BENCH_CPU_SAMPLES", BLOCK * 14000)       # 57 M samples ~ 10-15 s of CPU
+        got = h_out[:e2e_bytes].numpy()
+        want, per_block, kind = reference_bytes(pcm_np, C2)
+        parity = parity_record(got, h_flen[:nf.value].astype(np.int64), h_fbs[:nf.value].astype(np.int64),
+                               want, per_block, C2, kind)
+        parity["md5_matches_pcm"] = (md5_hex == hashlib.md5(pcm_np.astype("<i2").tobytes()).hexdigest())
+    except Exception as exc:
+        parity = {"frames_compared": 0, "error": str(exc)[:300]}
+
+    # ---- CPU baseline: the compiled reference on ONE host core, bounded sample --------
+    try:
+        budget = env_int("FLAKE_BENCH_CPU_SAMPLES", BLOCK * 14000)       # 57 M samples ~ 5 s of CPU
         budget = min(budget, nsamples // BLOCK * BLOCK)
-        total, times, kind = cpu_encode_threads(pcm_np[:budget], 1, 1, 0)
+        total, times, kind, _ = cpu_reference_time(pcm_np[:budget], C2, 1, 1, 0)
         cpu = {"value": round(total / times[0] / 1e6, 3), "unit": "MSamples/s", "cores": 1, "kind": kind,
                "sample": "first %d samples (%.0f s of audio) of rank 0's stream, one flake_encode_frame "
-                         "loop, 1 thread" % (total, total / RATE),
+                         "loop in C, 1 thread" % (total, total / RATE),
                "host_cores_available": os.cpu_count()}
     except Exception as exc:       # the baseline is informative; never fail the bench on it
         cpu = {"value": None, "unit": "MSamples/s", "cores": 1, "kind": "unavailable", "sample": str(exc)}
 
+    # ---- the other BASELINE.json configurations -----------------------------------------
+    others = {}
+    dp.close()
+    del dp, h_pcm32, pcm_pinned
+    if not os.environ.get("FLAKE_BENCH_SKIP_OTHERS"):
+        for name in ("C1", "C3", "C4"):
+            try:
+                others[name] = run_other_config(lib, name, dev, stream, peak_gbs, peak_src, traffic, torch)
+            except Exception as exc:
+                others[name] = {"error": str(exc)[:300]}
+
     line = {
         "metric": "MSamples/s encoded, flake -8", "value": round(value, 2), "unit": "MSamples/s",
+        "value_scope": "kernels only: PCM and outputs resident in HBM, no copies, no MD5 (e2e is the like-for-like figure)",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
@@ -514,20 +593,72 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms_max, 2),
                 "input": "int32 interleaved host buffer (flake_encode_frame convention)",
                 "includes": "H2D, all kernels, D2H of frames+lengths, MD5 of the PCM, final STREAMINFO",
-                "md5": md5_hex},
-        "e2e_multi_stream": multi,
+                "md5": md5_hex,
+                "md5_thread_ms": round(e2e_stats.md5_ms / (1 + e2e_steps), 1),
+                "gpu_ms": round(e2e_stats.gpu_ms / (1 + e2e_steps), 1),
+                "wall": "one stream's MD5 is a serial chain on one host core; see md5_thread_ms"},
+        "parity": parity,
+        "e2e_corpus": corpus,
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "other_configs": others,
         "frames_per_step": frames, "compressed_bytes_per_step": out_bytes,
         "compression_ratio": round(out_bytes / float(nsamples * CHANNELS * 2), 4),
         "step_ms": [round(x, 2) for x in step_ms],
+        "rank_ms_per_step": rank_ms,
     }
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    enc.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_other_config(lib, name, dev, stream, peak_gbs, peak_src, traffic, torch):
+    """Device-resident rate, stage times and roofline of C1 / C3 / C4, and whole-stream parity of
+    the host-buffer path against the reference."""
+    cfg = CONFIGS[name]
+    n = env_int("FLAKE_BENCH_%s_SAMPLES" % name, cfg["samples"])
+    pcm = workload_pcm(cfg, 0, n)
+    dp = DevicePass(lib, cfg, pcm, dev, stream)
+    steps = 5
+    for _ in range(3):
+        dp.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        dp.run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    stages = dp.stage_profile(3)
+    frames, out_bytes = dp.totals()
+    in_bps = cfg["ch"] * ((cfg["bps"] + 7) // 8)
+    roof = roofline_record(stages, 3, n, dp.nchunks, in_bps, out_bytes, peak_gbs, peak_src,
+                           (traffic or {}).get(name) if traffic else None)
+    dp.close()
+    del dp
+    rec = {"workload": name + ": " + cfg["what"], "samples": n, "value": round(n / (ms * 1e-3) / 1e6, 2),
+           "unit": "MSamples/s", "channel_msamples_per_s": round(cfg["ch"] * n / (ms * 1e-3) / 1e6, 2),
+           "ms_per_step": round(ms, 3), "steps": steps, "frames": frames, "compressed_bytes": out_bytes,
+           "compression_ratio": round(out_bytes / float(n * in_bps), 4), "roofline": roof}
+    try:
+        got, flen, fbs = host_encode(lib, cfg, pcm)
+        want, per_block, kind = reference_bytes(pcm, cfg)
+        rec["parity"] = parity_record(got, flen.astype(np.int64), fbs.astype(np.int64), want, per_block, cfg, kind)
+    except Exception as exc:
+        rec["parity"] = {"frames_compared": 0, "error": str(exc)[:300]}
+    return rec
+
+
+def run_corpus_leg(lib, api, pcm_pinned, nsamples, world, torch):
+    """A FIXED corpus of 1 h C2 streams through flake_b200_encode_corpus, ONE process driving
+    `world` GPUs with library-owned threads (strong scaling over --gpus; the other ranks idle)."""
+    from flake_b200 import corpus as fc
+    nstreams = env_int("FLAKE_BENCH_CORPUS_STREAMS", 16)
+    ngpu = min(world, torch.cuda.device_count())
+    return fc.bench_corpus(lib, pcm_pinned, nsamples, CHANNELS, RATE, BPS, LEVEL, nstreams, list(range(ngpu)))
 
 
 def main():

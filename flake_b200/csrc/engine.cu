@@ -168,9 +168,12 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
         if (ce_ == cudaSuccess) ce_ = cudaMemcpy(e->d_crc16tab, tab, sizeof tab, cudaMemcpyHostToDevice);
         if (ce_ != cudaSuccess) { set_err(err, errlen, "CRC table upload failed", ce_); fb_engine_destroy(e); return nullptr; }
     }
-    cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
-    cudaFuncSetAttribute(k_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->search_smem_ints * 4);
-    cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, e->pack_smem_words * 4);
+    /* The attribute is per function, per device and per PROCESS, not per engine: every engine sets
+     * the same constant (the staging budget), so a later engine with smaller blocks can never
+     * lower it under a live engine's launch size. */
+    cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { set_err(err, errlen, "cudaFuncSetAttribute failed", ce); fb_engine_destroy(e); return nullptr; }
     return e;

@@ -102,6 +102,26 @@ def synth_pcm(nsamples: int, channels: int = 2, bps: int = 16, sample_rate: int 
     return np.ascontiguousarray(q)
 
 
+def long_pcm(nsamples: int, channels: int, bps: int, sample_rate: int, seed: int = 0,
+             base_seconds: float = 40.0) -> np.ndarray:
+    """A long stream (minutes to hours) assembled from ONE `base_seconds` synthetic segment
+    (synth_pcm, "mix") repeated with a different gain per tile, so that generating an hour of
+    audio costs seconds of CPU.  Every tile is distinct data (the gain changes every sample
+    value and tile boundaries do not fall on block boundaries).  This is the generator of the
+    benchmark workloads: the GPU arm, the reference arm and the full-size parity tests all
+    call it, so that they encode the same samples."""
+    n0 = int(round(sample_rate * base_seconds))       # always the whole segment: a shorter request is a prefix
+    base = synth_pcm(n0, channels, bps, sample_rate, seed=seed).astype(np.float64)
+    reps = (nsamples + n0 - 1) // n0
+    rng = np.random.Generator(np.random.PCG64(SEED_BASE + 7919 * (seed + 1)))
+    out = np.empty((nsamples, channels), dtype=np.int32)
+    for r in range(reps):
+        g = float(rng.uniform(0.3, 1.0))
+        a, b = r * n0, min(nsamples, (r + 1) * n0)
+        out[a:b] = np.rint(base[:b - a] * g).astype(np.int32)
+    return out
+
+
 def pack_pcm(pcm: np.ndarray, bps: int) -> bytes:
     """Little-endian packed sample bytes at ceil(bps/8) bytes per sample (WAV data chunk)."""
     nbytes = (bps + 7) // 8

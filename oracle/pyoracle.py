@@ -176,3 +176,40 @@ def ref_library():
     if not have_ref():
         raise FileNotFoundError(REF_SO)
     return load_library(REF_SO, extension=False)
+
+
+def ref_encode_parallel(pcm: np.ndarray, sample_rate: int, bps: int, level: int, threads: int = 0,
+                        **overrides):
+    """The compiled reference over a whole stream, in C (oracle/ref_shim.c): `threads`
+    contiguous block ranges, one reference context per range with its frame counter set
+    to the serial encoder's value there, frames concatenated in order -- i.e. exactly the
+    bytes the flake/flake.c loop writes after the header.  threads=0: all host cores.
+    Returns (frame_bytes (np.uint8), bytes_per_block (np.uint32), max_frame_size)."""
+    from flake_b200.api import FlakeEncodeParams
+    ref = ref_library()
+    fn = ref.refshim_encode_parallel
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(FlakeEncodeParams), C.c_void_p, C.c_uint64, C.c_int,
+                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+    n, ch = pcm.shape
+    prm = FlakeEncodeParams()
+    prm.compression = level
+    if ref.flake_set_defaults(C.byref(prm)):
+        raise ValueError("bad level")
+    for k, v in overrides.items():
+        if v is not None:
+            setattr(prm, k, int(v))
+    bs = int(prm.block_size)
+    nblocks = (n + bs - 1) // bs
+    cap = n * ch * ((bps + 7) // 8) + (nblocks + 1) * (96 * (8 if prm.variable_block_size else 1) + 64) + n // 8 + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    clen = np.zeros(nblocks + 1, dtype=np.uint32)
+    nc, mx = C.c_uint32(0), C.c_uint32(0)
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    rc = fn(ch, sample_rate, bps, C.byref(prm), pcm.ctypes.data, n, threads, out.ctypes.data, cap,
+            clen.ctypes.data, nblocks + 1, C.byref(nc), C.byref(mx))
+    if rc < 0:
+        raise RuntimeError("reference encode failed")
+    return out[:rc], clen[:nc.value], mx.value

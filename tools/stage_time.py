@@ -19,7 +19,7 @@ lib.flake_b200_set_device(0)
 enc = api.Encoder(lib, 2, 44100, 16, n, level)
 enc.init()
 ctx = C.byref(enc.ctx)
-d_pcm = bench.synth_device(n, 0, dev)
+d_pcm = torch.from_numpy(bench.workload_pcm(bench.C2, 0, n).astype(np.int16)).to(dev)
 cs, cb, cf = C.c_ulonglong(), C.c_ulonglong(), C.c_uint()
 lib.flake_b200_device_capacity(ctx, C.byref(cs), C.byref(cb), C.byref(cf))
 chunk = int(cs.value); nch = (n + chunk - 1) // chunk

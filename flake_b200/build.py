@@ -26,6 +26,9 @@ NVCC_FLAGS = [
 ]
 
 
+HOST_C = ("flake_host.c", "md5.c", "md5_mb.c")      # the C host layer (gcc)
+
+
 def _run(cmd, cwd=None):
     r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
@@ -59,7 +62,7 @@ def build_product(force: bool = False, variant: str = "", defines=()) -> str:
     _run([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] +
          ["-I", inc, "-c", os.path.join(CSRC, "engine.cu"), "-o", obj_cu])
     objs = [obj_cu]
-    for c in ("flake_host.c", "md5.c"):
+    for c in HOST_C:
         o = os.path.join(libdir, c.replace(".c", ".o"))
         _run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-I", inc, "-I", CSRC,
               "-c", os.path.join(CSRC, c), "-o", o])
@@ -85,7 +88,7 @@ def build_emu(force: bool = False) -> str:
     o = os.path.join(EMUDIR, "cuda_emu.o")
     _run(["g++", "-std=c++17"] + common + ["-c", os.path.join(EMUDIR, "cuda_emu.cpp"), "-o", o])
     objs.append(o)
-    for c in ("flake_host.c", "md5.c"):
+    for c in HOST_C:
         o = os.path.join(EMUDIR, c.replace(".c", "_emu.o"))
         _run(["gcc", "-std=gnu11", "-O1", "-g", "-fPIC", "-Wall", "-I", inc, "-I", CSRC,
               "-c", os.path.join(CSRC, c), "-o", o])

@@ -36,6 +36,49 @@ __device__ __forceinline__ void fb_cp_async_wait_all(void)
 }
 #endif
 
+/* ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ----------------------
+ * cp.async.bulk (SASS: UBLKCP) moves a contiguous byte range with ONE instruction issued by
+ * one thread; the mbarrier counts the bytes that land (complete_tx).  Source, destination and
+ * size are multiples of 16 bytes.  The emulation copies at issue time and never waits. */
+#ifdef FLAKE_B200_CUDA_EMU
+typedef unsigned long long fb_mbar_t;
+static inline void fb_mbar_init(fb_mbar_t *bar, unsigned) { *bar = 0; }
+static inline void fb_mbar_init_fence(void) {}
+static inline void fb_mbar_expect_tx(fb_mbar_t *, unsigned) {}
+static inline void fb_bulk_g2s(void *dst_shared, const void *src_global, unsigned bytes, fb_mbar_t *) { memcpy(dst_shared, src_global, bytes); }
+static inline void fb_mbar_wait(fb_mbar_t *, unsigned) {}
+#else
+typedef unsigned long long fb_mbar_t;
+__device__ __forceinline__ void fb_mbar_init(fb_mbar_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+/* makes the initialised barrier visible to the async proxy before the first bulk copy */
+__device__ __forceinline__ void fb_mbar_init_fence(void)
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fb_mbar_expect_tx(fb_mbar_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fb_bulk_g2s(void *dst_shared, const void *src_global, unsigned bytes, fb_mbar_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst_shared)), "l"(src_global), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fb_mbar_wait(fb_mbar_t *bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+#endif
+
 /* marks a block as not speculatable, so that a rarely taken `if` stays a branch instead of
  * being turned into selects executed by every thread */
 #ifdef FLAKE_B200_CUDA_EMU

@@ -20,6 +20,9 @@
 #include "k_pack.cuh"
 
 #include <new>
+#include <map>
+#include <tuple>
+#include <vector>
 
 #define FB_SMEM_BUDGET (200 * 1024)
 #define FB_TIMING_RING 64
@@ -44,6 +47,7 @@ struct FbEngine {
     uint16_t *d_xpow32;             /* x^(32 j) mod P, CRC-16 chunk merge (k_pack) */
     uint32_t *d_crc16tab;           /* CRC-16 slicing tables [4][256] uint16 (k_pack) */
     unsigned long long *d_status;   /* look-back status per frame (k_pack) */
+    FbPlanNode *d_plan;             /* log-search decision tree (k_search), NULL for the other order methods */
     int search_smem_ints, pack_smem_words;
     uint64_t launches;
     /* optional per-kernel CUDA-event timing (bench.py roofline) */
@@ -53,6 +57,59 @@ struct FbEngine {
     uint64_t stage_launches[FB_NUM_STAGES];
     char err[256];
 };
+
+/* The decision tree of the log search for orders min_order..max_order with `group` candidates
+ * costed at a time -- see FbPlanNode (engine.h).  Steps are merged into one node while the
+ * candidate set of the next step is the same for every order that could be the best by then. */
+static uint16_t fb_plan_node(std::vector<FbPlanNode> &nodes, std::map<std::tuple<int, uint32_t, int>, uint16_t> &index,
+                             int lo, int hi, int group, int step, uint32_t done, int opt)
+{
+    if (step == 0) return (uint16_t)FB_PLAN_END;
+    const auto key = std::make_tuple(step, done, opt);
+    const auto it = index.find(key);
+    if (it != index.end()) return it->second;
+    const uint16_t idx = (uint16_t)nodes.size();
+    index[key] = idx;
+    nodes.push_back(FbPlanNode());
+    const uint32_t range = (hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+    uint32_t ord = 0, gmask = 0, hyp = 1u << opt;
+    int cnt = 0, nsteps = 0, members[FB_PLAN_CHILDREN];
+    for (int s = step; s > 0; s >>= 1) {
+        uint32_t cor = 0, cand = 0xffffffffu;
+        for (int h = 0; h < 32; h++) {
+            if (!((hyp >> h) & 1u)) continue;
+            uint32_t cm = 1u << h;
+            if (h - s >= 0) cm |= 1u << (h - s);
+            if (h + s < 32) cm |= 1u << (h + s);
+            cm &= range & ~(done | gmask);
+            cor |= cm; cand &= cm;
+        }
+        if (cor != cand || cnt + __builtin_popcount(cor) > group) break;
+        for (int b = 0; b < 32; b++)
+            if ((cor >> b) & 1u) { ord |= (uint32_t)(b + 1) << (8 * cnt); members[cnt++] = b; }
+        gmask |= cor; hyp |= cor; nsteps++;
+    }
+    FbPlanNode nd;
+    memset(&nd, 0, sizeof nd);
+    nd.ord = ord; nd.cnt = (uint16_t)cnt; nd.nsteps = (uint16_t)nsteps;
+    for (int i = 0; i < FB_PLAN_CHILDREN; i++) nd.child[i] = (uint16_t)FB_PLAN_END;
+    nd.child[0] = fb_plan_node(nodes, index, lo, hi, group, step >> nsteps, done | gmask, opt);
+    for (int i = 0; i < cnt; i++)
+        nd.child[1 + i] = fb_plan_node(nodes, index, lo, hi, group, step >> nsteps, done | gmask, members[i]);
+    nodes[idx] = nd;
+    return idx;
+}
+
+static std::vector<FbPlanNode> fb_build_log_plan(int min_order, int max_order, int group)
+{
+    std::vector<FbPlanNode> nodes;
+    std::map<std::tuple<int, uint32_t, int>, uint16_t> index;
+    const int lo = min_order - 1, hi = max_order - 1;
+    const int start = lo + (max_order - min_order) / 3;
+    fb_plan_node(nodes, index, lo, hi, group, 16, 0u, start);
+    nodes[0].start_order = (uint16_t)start;
+    return nodes;
+}
 
 static void set_err(char *dst, size_t n, const char *msg, cudaError_t ce)
 {
@@ -109,7 +166,6 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     FB_TRY_ALLOC(e->d_nframes, sizeof(uint32_t) * 4);
     FB_TRY_ALLOC(e->d_subs, sizeof(FbSub) * (size_t)e->max_subs);
     FB_TRY_ALLOC(e->d_modes, (size_t)e->max_frames);
-    FB_TRY_ALLOC(e->d_smp, sizeof(int32_t) * nint);
     FB_TRY_ALLOC(e->d_res, sizeof(int32_t) * nint);
     FB_TRY_ALLOC(e->d_slots, e->slot_bytes);
     FB_TRY_ALLOC(e->d_frame_len, sizeof(uint32_t) * (size_t)e->max_frames);
@@ -130,6 +186,9 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
         const int group = (cfg->prediction_type == 2 && cfg->max_order > 12) ? FB_GROUP_OF(32) : FB_GROUP_OF(12);
         const int words = fb_search_smem_words(B, group);
         e->search_smem_ints = ((size_t)words * 4 <= FB_SMEM_BUDGET) ? words : 0;
+        /* int32 planes exist in global memory only for more than two channels (k_prep deinterleaves
+         * once, fb_uses_planes) and as k_search's scratch for blocks that do not fit shared memory */
+        if (!e->search_smem_ints || fb_uses_planes(C)) FB_TRY_ALLOC(e->d_smp, sizeof(int32_t) * nint);
     }
     {
         const uint64_t capb = 64u + (((uint64_t)B * (uint64_t)(C * cfg->bps + 1) + 7u) >> 3);
@@ -168,6 +227,13 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
         if (ce_ == cudaSuccess) ce_ = cudaMemcpy(e->d_crc16tab, tab, sizeof tab, cudaMemcpyHostToDevice);
         if (ce_ != cudaSuccess) { set_err(err, errlen, "CRC table upload failed", ce_); fb_engine_destroy(e); return nullptr; }
     }
+    if (cfg->prediction_type == 2 && cfg->order_method == 6) {
+        const int group = cfg->max_order > 12 ? FB_GROUP_OF(32) : FB_GROUP_OF(12);
+        const std::vector<FbPlanNode> plan = fb_build_log_plan(cfg->min_order, cfg->max_order, group);
+        cudaError_t ce_ = cudaMalloc((void **)&e->d_plan, plan.size() * sizeof(FbPlanNode));
+        if (ce_ == cudaSuccess) ce_ = cudaMemcpy(e->d_plan, plan.data(), plan.size() * sizeof(FbPlanNode), cudaMemcpyHostToDevice);
+        if (ce_ != cudaSuccess) { set_err(err, errlen, "search plan upload failed", ce_); fb_engine_destroy(e); return nullptr; }
+    }
     /* The attribute is per function, per device and per PROCESS, not per engine: every engine sets
      * the same constant (the staging budget), so a later engine with smaller blocks can never
      * lower it under a live engine's launch size. */
@@ -186,7 +252,7 @@ extern "C" void fb_engine_destroy(FbEngine *e)
     cudaFree(e->d_frames); cudaFree(e->d_nframes); cudaFree(e->d_subs); cudaFree(e->d_modes);
     cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
     cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
-    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32); cudaFree(e->d_crc16tab); cudaFree(e->d_status);
+    cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32); cudaFree(e->d_crc16tab); cudaFree(e->d_status); cudaFree(e->d_plan);
     if (e->tev[0][0])
         for (int p = 0; p < FB_TIMING_RING; p++)
             for (int i = 0; i <= FB_NUM_STAGES; i++) cudaEventDestroy(e->tev[p][i]);
@@ -242,41 +308,62 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
         e->launches += 1;
     }
     FB_MARK(1);
+    const unsigned long long pcm_bytes = (unsigned long long)ns * (unsigned long long)cfg.channels *
+                                         (unsigned long long)(fmt == FB_PCM_S16LE ? 2 : fmt == FB_PCM_S24LE ? 3 : fmt == FB_PCM_S8 ? 1 : 4);
     FB_LAUNCH(k_prep, dim3(grid_frames), dim3(FB_PREP_THREADS), 0, st,
-              cfg, d_pcm, fmt, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_modes);
+              cfg, d_pcm, fmt, pcm_bytes, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_modes);
     e->launches += 1;
     FB_MARK(2);
     if (cfg.prediction_type == 2) {
         /* a lane pair per subframe; the register ring is sized by the template (lags 0..ML) */
         const dim3 lpc_grid((grid_subs + FB_LPC_SUBS_PER_CTA - 1) / FB_LPC_SUBS_PER_CTA);
-#define FB_LPC_GO(ML_)                                                                          \
-        FB_LAUNCH(k_lpc<ML_>, lpc_grid, dim3(FB_LPC_THREADS), 0, st,                              \
-                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_coefs, e->d_shifts)
+        /* stereo 16/24-bit layouts have a loader of their own (one load per sample pair, branch
+         * free); specialised for the orders the presets use */
+        int lk = FB_LPC_LK_GENERIC;
+        if (cfg.channels == 2 && fmt == FB_PCM_S16LE && (((size_t)d_pcm) & 3u) == 0) lk = FB_LPC_LK_S16_STEREO;
+        if (cfg.channels == 2 && fmt == FB_PCM_S24LE && (((size_t)d_pcm) & 1u) == 0) lk = FB_LPC_LK_S24_STEREO;
+        if (fb_uses_planes(cfg.channels)) lk = FB_LPC_LK_PLANES;
+#define FB_LPC_GO2(ML_, LK_)                                                                      \
+        FB_LAUNCH((k_lpc<ML_, LK_>), lpc_grid, dim3(FB_LPC_THREADS), 0, st,                       \
+                  cfg, e->d_frames, e->d_nframes, d_pcm, fmt, e->d_smp, e->d_modes, e->d_subs, e->d_coefs, e->d_shifts)
+#define FB_LPC_GO(ML_)                                                                            \
+        do {                                                                                      \
+            if (lk == FB_LPC_LK_PLANES) FB_LPC_GO2(ML_, FB_LPC_LK_PLANES);                        \
+            else FB_LPC_GO2(ML_, FB_LPC_LK_GENERIC);                                              \
+        } while (0)
+#define FB_LPC_GO3(ML_)                                                                           \
+        do {                                                                                      \
+            if (lk == FB_LPC_LK_S16_STEREO) FB_LPC_GO2(ML_, FB_LPC_LK_S16_STEREO);                \
+            else if (lk == FB_LPC_LK_S24_STEREO) FB_LPC_GO2(ML_, FB_LPC_LK_S24_STEREO);           \
+            else FB_LPC_GO(ML_);                                                                  \
+        } while (0)
         if (cfg.max_order <= 4) FB_LPC_GO(4);
-        else if (cfg.max_order <= 8) FB_LPC_GO(8);
-        else if (cfg.max_order <= 12) FB_LPC_GO(12);
+        else if (cfg.max_order <= 8) FB_LPC_GO3(8);
+        else if (cfg.max_order <= 12) FB_LPC_GO3(12);
         else if (cfg.max_order <= 16) FB_LPC_GO(16);
         else if (cfg.max_order <= 24) FB_LPC_GO(24);
-        else FB_LPC_GO(32);
+        else FB_LPC_GO3(32);
+#undef FB_LPC_GO3
+#undef FB_LPC_GO2
 #undef FB_LPC_GO
         e->launches += 1;
     }
     FB_MARK(3);
     if (cfg.prediction_type == 2 && cfg.max_order > 12) {
         FB_LAUNCH(k_search<32>, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
-                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_coefs, e->d_shifts,
-                  e->search_smem_ints);
+                  cfg, e->d_frames, e->d_nframes, d_pcm, fmt, pcm_bytes, e->d_modes, e->d_smp, e->d_res, e->d_subs,
+                  e->d_coefs, e->d_shifts, e->d_plan, e->search_smem_ints);
     } else {
         FB_LAUNCH(k_search<12>, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
-                  cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_coefs, e->d_shifts,
-                  e->search_smem_ints);
+                  cfg, e->d_frames, e->d_nframes, d_pcm, fmt, pcm_bytes, e->d_modes, e->d_smp, e->d_res, e->d_subs,
+                  e->d_coefs, e->d_shifts, e->d_plan, e->search_smem_ints);
     }
     FB_MARK(4);
     /* threads per frame by the work in it (measured: 8192 samples per frame 1.75 ms with 128 threads vs
      * 1.88 with 256 per C2 stream; 32768 samples per frame 2.79 vs 2.08) */
     const int pack_threads = (uint64_t)B * (uint64_t)cfg.channels >= 16384u ? FB_PACK_THREADS : FB_PACK_THREADS / 2;
     FB_LAUNCH(k_pack, dim3(grid_frames), dim3(pack_threads), (size_t)e->pack_smem_words * 4, st,
-              cfg, e->d_frames, e->d_nframes, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
+              cfg, e->d_frames, e->d_nframes, d_pcm, fmt, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
               flen, d_frame_bs, e->pack_smem_words, e->d_xpow32, e->d_crc16tab,
               e->d_nframes + 2, e->d_status, e->d_frame_off, (uint8_t *)d_out, d_summary);
     FB_MARK(5);
@@ -367,6 +454,21 @@ extern "C" void *fb_cuda_event_create(void)
 {
     cudaEvent_t ev = nullptr;
     return cudaEventCreate(&ev) == cudaSuccess ? (void *)ev : nullptr;
+}
+/* for host threads that wait on the GPU while other threads need the cores (MD5 of a corpus):
+ * cudaEventSynchronize on such an event yields the CPU instead of spinning */
+extern "C" void *fb_cuda_event_create_blocking(void)
+{
+    cudaEvent_t ev = nullptr;
+    return cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess ? (void *)ev : nullptr;
+}
+/* 1 when `p` is page-locked host memory the copy engines can reach directly (cudaMallocHost /
+ * cudaHostRegister), 0 for pageable memory */
+extern "C" int fb_cuda_host_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return at.type == cudaMemoryTypeHost ? 1 : 0;
 }
 extern "C" void fb_cuda_event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
 extern "C" int fb_cuda_event_record(void *ev, void *s) { return cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)s) == cudaSuccess ? 0 : -1; }

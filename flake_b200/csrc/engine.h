@@ -68,6 +68,24 @@ typedef struct FbSummary {
     uint32_t reserved;
 } FbSummary;
 
+/*
+ * One node of the log-search plan (optimize.c:241-261).  The candidate orders the search costs
+ * next depend only on (step, orders costed so far, best order so far), never on the samples, so
+ * the whole decision tree is tabulated once per engine on the host (engine.cu,
+ * fb_build_log_plan) and k_search walks it: cost `cnt` candidates (`ord`: 8 bits each, the
+ * orders of `nsteps` consecutive steps that do not depend on each other's outcome), replay the
+ * steps on the totals, continue at child[0] when the best order did not change or at
+ * child[1 + s] when candidate s became the best.  0xffff ends the search.
+ */
+#define FB_PLAN_CHILDREN 5
+#define FB_PLAN_END 0xffffu
+typedef struct FbPlanNode {
+    uint32_t ord;
+    uint16_t cnt, nsteps;
+    uint16_t child[FB_PLAN_CHILDREN];
+    uint16_t start_order;       /* node 0 only: the 0-based order the search starts from */
+} FbPlanNode;
+
 typedef struct FbEngine FbEngine;
 
 /* device < 0: current device.  max_blocks: chunk capacity in blocks. */
@@ -121,6 +139,8 @@ int   fb_cuda_stream_sync(void *s);
 int   fb_cuda_h2d(void *d, const void *h, size_t n, void *stream);
 int   fb_cuda_d2h(void *h, const void *d, size_t n, void *stream);
 void *fb_cuda_event_create(void);
+void *fb_cuda_event_create_blocking(void);    /* waits yield the CPU; no timing */
+int   fb_cuda_host_is_pinned(const void *p);  /* page-locked host memory? */
 void  fb_cuda_event_destroy(void *ev);
 int   fb_cuda_event_record(void *ev, void *stream);
 int   fb_cuda_event_sync(void *ev);

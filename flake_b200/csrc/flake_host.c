@@ -17,6 +17,7 @@
 #include "flake_b200.h"
 #include "engine.h"
 #include "md5.h"
+#include "flake_host_int.h"
 
 #include <pthread.h>
 #include <stdio.h>
@@ -26,8 +27,6 @@
 
 #define FB_VERSION "SVN"
 #define FB_FALLBACK_CHUNK_BLOCKS 2048
-#define FB_CHUNK_DEVICE_INTS (320u << 20)     /* channel-samples per pass: device-resident API, stream length known */
-#define FB_CHUNK_HOST_INTS (80u << 20)        /* host streaming path (pipelined lanes), or length unknown */
 
 typedef struct FbLane {
     void *h_in, *d_in;              /* pinned staging + device copy of the chunk's PCM */
@@ -71,7 +70,7 @@ static int g_device = -2;           /* -2: not chosen yet */
 struct FbCtx;
 static int default_chunk_blocks(const struct FbCtx *c, unsigned int stream_samples, uint64_t target_ints);
 
-static double now_ms(void)
+double fb_now_ms(void)
 {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -338,7 +337,7 @@ static int lane_alloc(FbLane *l, const FbEngine *e, const FbConfig *cfg, void *h
     return 0;
 }
 
-static size_t pcm_bytes_per_sample(int fmt)
+size_t fb_pcm_container_bytes(int fmt)
 {
     switch (fmt) {
     case FLAKE_B200_PCM_S16LE: return 2;
@@ -355,7 +354,7 @@ static size_t pcm_bytes_per_sample(int fmt)
  * ingest reproduces the int32 exactly); 0 when some sample is out of range and the
  * encoder must see the caller's int32 values untouched.
  */
-static int pack_s32(const int32_t *src, size_t count, int bytes, uint8_t *dst)
+int fb_pack_s32(const int32_t *src, size_t count, int bytes, uint8_t *dst)
 {
     int32_t bad = 0;
     if (bytes == 2) {
@@ -393,14 +392,14 @@ static void lane_stage(FbCtx *c, FbLane *l, const void *pcm, int fmt, uint64_t n
     l->pack_bytes = 0;
     if (fmt == FLAKE_B200_PCM_S32) {
         const int bytes = (c->bps + 7) >> 3;
-        const int lossless = pack_s32((const int32_t *)pcm, count, bytes, (uint8_t *)l->h_pack);
+        const int lossless = fb_pack_s32((const int32_t *)pcm, count, bytes, (uint8_t *)l->h_pack);
         l->pack_bytes = count * (size_t)bytes;
         if (lossless) {
             *upload = l->h_pack; *upload_bytes = l->pack_bytes; *upload_fmt = packed_format(bytes);
             return;
         }
     }
-    const size_t bytes = count * pcm_bytes_per_sample(fmt);
+    const size_t bytes = count * fb_pcm_container_bytes(fmt);
     memcpy(l->h_in, pcm, bytes);
     *upload = l->h_in; *upload_bytes = bytes; *upload_fmt = fmt;
 }
@@ -477,10 +476,45 @@ int flake_b200_set_device(int device)
     return 0;
 }
 
-int flake_encode_init(FlakeContext *s)
+/* FbConfig of a context's public fields: the frame-header codes of encode.c:400-434 and the
+ * encoding parameters.  Shared by flake_encode_init and flake_b200_encode_corpus. */
+void fb_config_from_context(const FlakeContext *s, FbConfig *g)
 {
     static const int rates[16] = {0, 0, 0, 0, 8000, 16000, 22050, 24000, 32000, 44100, 48000, 96000, 0, 0, 0, 0};
     static const int depths[8] = {0, 8, 12, 0, 16, 20, 24, 0};
+    const FlakeEncodeParams *p = &s->params;
+    memset(g, 0, sizeof *g);
+    g->channels = s->channels; g->bps = s->bits_per_sample; g->block_size = p->block_size;
+    g->sr_code0 = 0; g->sr_code1 = 0;
+    int i;
+    for (i = 4; i < 12; i++) if (s->sample_rate == rates[i]) { g->sr_code0 = i; break; }
+    if (i == 12) {                                          /* encode.c:410-422 */
+        if (s->sample_rate % 1000 == 0 && s->sample_rate <= 255000) { g->sr_code0 = 12; g->sr_code1 = s->sample_rate / 1000; }
+        else if (s->sample_rate % 10 == 0 && s->sample_rate <= 655350) { g->sr_code0 = 14; g->sr_code1 = s->sample_rate / 10; }
+        else if (s->sample_rate < 65535) { g->sr_code0 = 13; g->sr_code1 = s->sample_rate; }
+    }
+    g->bps_code = 0;
+    for (i = 1; i < 8; i++) if (s->bits_per_sample == depths[i]) { g->bps_code = i; break; }
+    g->order_method = p->order_method;
+    g->stereo_method = p->stereo_method;
+    g->prediction_type = p->prediction_type;
+    g->min_order = p->min_prediction_order;
+    g->max_order = p->max_prediction_order;
+    g->min_porder = p->min_partition_order;
+    g->max_porder = p->max_partition_order;
+    g->variable_block_size = p->variable_block_size;
+    g->allow_vbs = p->allow_vbs;
+}
+
+/* verbatim bound of a full block, encode.c:446-450: the seed of STREAMINFO's maximum frame size */
+int fb_verbatim_bound(const FbConfig *g)
+{
+    if (g->channels == 2) return 16 + ((g->block_size * (2 * g->bps + 1) + 7) >> 3);
+    return 16 + ((g->block_size * g->channels * g->bps + 7) >> 3);
+}
+
+int flake_encode_init(FlakeContext *s)
+{
     if (!s) return -1;
     s->header = NULL;
     s->private_ctx = NULL;
@@ -497,30 +531,9 @@ int flake_encode_init(FlakeContext *s)
     c->sample_count = s->samples;
 
     FbConfig *g = &c->cfg;
-    g->channels = c->channels; g->bps = c->bps; g->block_size = c->params.block_size;
-    g->sr_code0 = 0; g->sr_code1 = 0;
-    int i;
-    for (i = 4; i < 12; i++) if (c->samplerate == rates[i]) { g->sr_code0 = i; break; }
-    if (i == 12) {                                          /* encode.c:410-422 */
-        if (c->samplerate % 1000 == 0 && c->samplerate <= 255000) { g->sr_code0 = 12; g->sr_code1 = c->samplerate / 1000; }
-        else if (c->samplerate % 10 == 0 && c->samplerate <= 655350) { g->sr_code0 = 14; g->sr_code1 = c->samplerate / 10; }
-        else if (c->samplerate < 65535) { g->sr_code0 = 13; g->sr_code1 = c->samplerate; }
-    }
-    g->bps_code = 0;
-    for (i = 1; i < 8; i++) if (c->bps == depths[i]) { g->bps_code = i; break; }
-    g->order_method = c->params.order_method;
-    g->stereo_method = c->params.stereo_method;
-    g->prediction_type = c->params.prediction_type;
-    g->min_order = c->params.min_prediction_order;
-    g->max_order = c->params.max_prediction_order;
-    g->min_porder = c->params.min_partition_order;
-    g->max_porder = c->params.max_partition_order;
-    g->variable_block_size = c->params.variable_block_size;
-    g->allow_vbs = c->params.allow_vbs;
+    fb_config_from_context(s, g);
 
-    /* verbatim bound of a full block, encode.c:446-450 */
-    if (c->channels == 2) c->max_frame_size = 16 + ((g->block_size * (2 * c->bps + 1) + 7) >> 3);
-    else c->max_frame_size = 16 + ((g->block_size * c->channels * c->bps + 7) >> 3);
+    c->max_frame_size = fb_verbatim_bound(g);
 
     /* header first: the reference serialises STREAMINFO before md5_init() on a
      * zeroed context (encode.c:391, 458-469), so the provisional digest is
@@ -645,9 +658,9 @@ static void *md5_worker(void *arg)
 {
     Md5Pipe *p = (Md5Pipe *)arg;
     if (p->direct) {
-        const double t0 = now_ms();
+        const double t0 = fb_now_ms();
         fb_md5_update(p->md5, p->direct, p->direct_bytes);
-        p->ms = now_ms() - t0;
+        p->ms = fb_now_ms() - t0;
         return NULL;
     }
     for (uint64_t k = 0; k < p->total; k++) {
@@ -655,9 +668,9 @@ static void *md5_worker(void *arg)
         while (p->produced <= k) pthread_cond_wait(&p->cv, &p->mu);
         const void *ptr = p->ptr[k & 1]; const size_t len = p->len[k & 1];
         pthread_mutex_unlock(&p->mu);
-        const double t0 = now_ms();
+        const double t0 = fb_now_ms();
         fb_md5_update(p->md5, ptr, len);
-        p->ms += now_ms() - t0;
+        p->ms += fb_now_ms() - t0;
         pthread_mutex_lock(&p->mu);
         p->consumed = k + 1;
         pthread_cond_broadcast(&p->cv);
@@ -678,21 +691,26 @@ static void *md5_worker(void *arg)
  * Streams shorter than that get an engine of their own size.  FLAKE_B200_CHUNK_BLOCKS and
  * flake_b200_set_chunk_blocks() override both.
  */
-static int default_chunk_blocks(const FbCtx *c, unsigned int stream_samples, uint64_t target_ints)
+int fb_chunk_blocks_for(int device, int block_size, int channels, uint64_t stream_samples, uint64_t target_ints)
 {
     const char *cb = getenv("FLAKE_B200_CHUNK_BLOCKS");
     if (cb && atoi(cb) >= 1) return atoi(cb);
-    const uint64_t per_block = (uint64_t)c->params.block_size * (uint64_t)c->channels;
-    const int sms = fb_cuda_sm_count(c->device);
+    const uint64_t per_block = (uint64_t)block_size * (uint64_t)channels;
+    const int sms = fb_cuda_sm_count(device);
     uint64_t blocks = target_ints / (per_block ? per_block : 1);
     if (sms > 0 && blocks >= (uint64_t)sms) blocks -= blocks % (uint64_t)sms;
     if (blocks < 1) blocks = 1;
     if (sms <= 0 && blocks > FB_FALLBACK_CHUNK_BLOCKS) blocks = FB_FALLBACK_CHUNK_BLOCKS;
     if (stream_samples) {
-        const uint64_t need = ((uint64_t)stream_samples + (uint64_t)c->params.block_size - 1) / (uint64_t)c->params.block_size;
+        const uint64_t need = (stream_samples + (uint64_t)block_size - 1) / (uint64_t)block_size;
         if (need < blocks) blocks = need;
     }
     return (int)blocks;
+}
+
+static int default_chunk_blocks(const FbCtx *c, unsigned int stream_samples, uint64_t target_ints)
+{
+    return fb_chunk_blocks_for(c->device, c->params.block_size, c->channels, stream_samples, target_ints);
 }
 
 int flake_b200_set_chunk_blocks(FlakeContext *s, int blocks)
@@ -757,10 +775,10 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
     int rc = ensure_batch_engine(c);
     if (rc) return rc;
 
-    const double t0 = now_ms();
+    const double t0 = fb_now_ms();
     const uint64_t B = (uint64_t)c->params.block_size;
     const uint64_t chunk = (uint64_t)c->chunk_blocks * B;
-    const size_t bps_in = pcm_bytes_per_sample(fmt) * (size_t)c->channels;   /* bytes per inter-channel sample */
+    const size_t bps_in = fb_pcm_container_bytes(fmt) * (size_t)c->channels;   /* bytes per inter-channel sample */
     const uint64_t nchunks = (nsamples + chunk - 1) / chunk;
 
     /* MD5 runs beside the GPU for the whole call */
@@ -771,7 +789,7 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
     pipe.total = nchunks;
     pthread_mutex_init(&pipe.mu, NULL);
     pthread_cond_init(&pipe.cv, NULL);
-    if (fmt != FLAKE_B200_PCM_S32 && pcm_bytes_per_sample(fmt) == (size_t)digest_bytes) {
+    if (fmt != FLAKE_B200_PCM_S32 && fb_pcm_container_bytes(fmt) == (size_t)digest_bytes) {
         pipe.direct = pcm;
         pipe.direct_bytes = (size_t)nsamples * bps_in;
     }
@@ -806,7 +824,7 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
             if (!pipe.direct) {
                 if (fmt != FLAKE_B200_PCM_S32) {
                     /* container wider/narrower than the digest layout: widen, then pack */
-                    const size_t cnt = (size_t)ns * (size_t)c->channels, have = pcm_bytes_per_sample(fmt);
+                    const size_t cnt = (size_t)ns * (size_t)c->channels, have = fb_pcm_container_bytes(fmt);
                     if (!widen) widen = (int32_t *)malloc(sizeof(int32_t) * (size_t)chunk * (size_t)c->channels);
                     if (widen) {
                         const uint8_t *q = src;
@@ -814,7 +832,7 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
                             widen[i] = have == 2 ? (int16_t)(q[0] | (q[1] << 8))
                                      : have == 3 ? (int32_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)(int8_t)q[2] << 16))
                                      : (int8_t)q[0];
-                        pack_s32(widen, cnt, digest_bytes, (uint8_t *)l->h_pack);
+                        fb_pack_s32(widen, cnt, digest_bytes, (uint8_t *)l->h_pack);
                         l->pack_bytes = cnt * (size_t)digest_bytes;
                     } else err = -3;
                 }
@@ -884,7 +902,7 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
     const float ms = fb_cuda_event_elapsed_ms(c->ev_a, c->ev_b);
     c->stats.gpu_ms += ms > 0 ? ms : 0;
     c->stats.md5_ms += job.ms;
-    c->stats.wall_ms += now_ms() - t0;
+    c->stats.wall_ms += fb_now_ms() - t0;
     return (long long)out_pos;
 }
 
@@ -902,8 +920,7 @@ int flake_b200_reset_stream(FlakeContext *s)
     c->frame_count = 0;
     c->last_frame = 0;
     fb_md5_init(&c->md5);
-    if (c->channels == 2) c->max_frame_size = 16 + ((c->cfg.block_size * (2 * c->bps + 1) + 7) >> 3);
-    else c->max_frame_size = 16 + ((c->cfg.block_size * c->channels * c->bps + 7) >> 3);
+    c->max_frame_size = fb_verbatim_bound(&c->cfg);
     memset(&c->stats, 0, sizeof c->stats);
     return 0;
 }

@@ -68,12 +68,6 @@ __device__ __forceinline__ double fb_windowed(int32_t xv, int p, int n, double c
     return __dmul_rn((double)xv, fb_welch(min(p, n - 1 - p), cc));
 }
 
-/* the sample the analysis sees at position p of a plane of n samples */
-__device__ __forceinline__ int32_t fb_lpc_sample(const int32_t *x, int p, int n)
-{
-    return (p >= 0 && p < n && !((n & 1) && p == (n >> 1))) ? x[p] : 0;
-}
-
 /* lpc.c:167-219 with precision 15 (encode.c:443).  `in` is modified like the reference's
  * row (the rescale branch).  `order` may differ per lane. */
 template <int ML>
@@ -144,16 +138,25 @@ __device__ __forceinline__ void fb_store_row(int32_t *co, int32_t *so, int rowi,
  * coefs_out: [subframe][32][32] int32 (row = order-1, entries 0..order-1 written),
  * shift_out: [subframe][32].  Grid: ceil(subframes / FB_LPC_SUBS_PER_CTA) CTAs.
  */
-template <int ML>
+/* how the tile loader reads the packed PCM */
+#define FB_LPC_LK_GENERIC    0   /* any layout: one (branchy) fb_pcm_sample per row and position */
+#define FB_LPC_LK_S16_STEREO 1   /* 16-bit stereo: ONE 32-bit load per sample pair serves both rows of a frame */
+#define FB_LPC_LK_S24_STEREO 2   /* 24-bit stereo: three 16-bit loads per sample pair */
+#define FB_LPC_LK_PLANES     3   /* more than two channels: k_prep's deinterleaved int32 planes (fb_uses_planes) */
+
+template <int ML, int LK>
 __global__ void __launch_bounds__(FB_LPC_THREADS)
-k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
-      FbSub *subs, int32_t *coefs_out, int32_t *shift_out)
+k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const void *pcm, int fmt,
+      const int32_t *planes, const uint8_t *ch_modes, FbSub *subs, int32_t *coefs_out, int32_t *shift_out)
 {
     typedef FbLpcGeom<ML> G;
     __shared__ int32_t s_rows[FB_LPC_WARPS][2][16 * FB_LPC_ROW];
-    __shared__ const int32_t *s_ptr[FB_LPC_WARPS][16];
+    __shared__ unsigned long long s_ebase[FB_LPC_WARPS][16];   /* interleaved element index of the frame's sample 0 */
     __shared__ int s_n[FB_LPC_WARPS][16];
     __shared__ int s_hole[FB_LPC_WARPS][16];          /* centre of an odd block, else -1 */
+    __shared__ int s_cmw[FB_LPC_WARPS][16];           /* channel | ch_mode << 8 | wasted bits << 16 */
+    __shared__ int s_nf[FB_LPC_WARPS][16];            /* samples of the row's frame (s_n is 0 for a row that needs no analysis) */
+    __shared__ int s_coef[FB_LPC_WARPS][16];          /* stereo rows: the transform as a linear form (fb_stereo_coef) */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ca = lane & 1, row = lane >> 1;
@@ -162,23 +165,37 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
     const uint32_t sf = blockIdx.x * FB_LPC_SUBS_PER_CTA + (uint32_t)(warp * 16 + row);
 
     /* same gate as optimize.c:143-193: only the LPC branch needs coefficients */
-    int n = 0;
-    const int32_t *x = smp;
+    /* The subframe's samples are read straight from the packed PCM: deinterleaved, decorrelated by
+     * the frame's stereo decision and shifted by the wasted bits on the fly (fb_pcm_sample). */
+    int n = 0, cmw = 0, nfr = 0;
+    size_t ebase = 0;
     FbSub *sb = nullptr;
     if (sf < nsubs) {
         const uint32_t f = sf / (uint32_t)C;
         const int c = (int)(sf % (uint32_t)C);
         const FbFrame fr = frames[f];
         sb = &subs[sf];
-        if (!(sb->is_const || fr.n < 5u || cfg.prediction_type != 2 || (int)fr.n <= lag)) {
-            n = (int)fr.n;
-            x = smp + (size_t)fr.start * C + (size_t)c * n;
-        }
+        nfr = (int)fr.n;
+        ebase = (size_t)fr.start * C;
+        if (LK == FB_LPC_LK_PLANES) ebase += (size_t)c * (size_t)nfr;     /* first word of the subframe's plane */
+        cmw = c | ((int)ch_modes[f] << 8) | (sb->wasted << 16);
+        if (!(sb->is_const || fr.n < 5u || cfg.prediction_type != 2 || (int)fr.n <= lag)) n = nfr;
     }
     const int nmax = (int)__reduce_max_sync(FB_FULL_MASK, (unsigned)n);
     if (nmax == 0) return;                               /* warp-uniform */
-    if (ca == 0) { s_ptr[warp][row] = x; s_n[warp][row] = n; s_hole[warp][row] = (n & 1) ? (n >> 1) : -1; }
+    if (ca == 0) {
+        s_ebase[warp][row] = ebase; s_n[warp][row] = n; s_nf[warp][row] = nfr;
+        s_hole[warp][row] = (nfr & 1) ? (nfr >> 1) : -1; s_cmw[warp][row] = cmw;
+        s_coef[warp][row] = fb_stereo_coef((cmw >> 8) & 0xff, cmw & 0xff, cmw >> 16);
+    }
     __syncwarp();
+    /* sample p of this lane pair's subframe as the analysis sees it (zero outside the block and at
+     * the centre of an odd block) */
+    auto x_at = [&](int p) -> int32_t {
+        if (!(p >= 0 && p < n && !((n & 1) && p == (n >> 1)))) return 0;
+        if (LK == FB_LPC_LK_PLANES) return planes[ebase + (size_t)p];
+        return fb_pcm_sample(pcm, fmt, ebase, C, cmw & 0xff, (cmw >> 8) & 0xff, cmw >> 16, p);
+    };
 
     const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
 
@@ -187,7 +204,7 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
     {
         double d0[ML + 1];
 #pragma unroll
-        for (int p = 0; p <= ML; p++) d0[p] = fb_windowed(fb_lpc_sample(x, p, n), p, n, cc);
+        for (int p = 0; p <= ML; p++) d0[p] = fb_windowed(x_at(p), p, n, cc);
 #pragma unroll
         for (int i = 0; i <= ML; i++) {
             double s = 1.0;
@@ -206,25 +223,70 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_
 #pragma unroll
     for (int k = 0; k < G::K; k++) {
         const int p = lag - 1 - k + ca;
-        D[k] = fb_windowed(fb_lpc_sample(x, p, n), p, n, cc);
+        D[k] = fb_windowed(x_at(p), p, n, cc);
     }
-    double other_prev = fb_windowed(fb_lpc_sample(x, lag, n), lag, n, cc);
+    double other_prev = fb_windowed(x_at(lag), lag, n, cc);
 
     const int P0 = lag + 1;
     const int ntiles = (nmax - P0 + G::TL - 1) / G::TL;
     int32_t pre[16 * G::LD];
     int32_t *rows0 = s_rows[warp][0], *rows1 = s_rows[warp][1];
 
+    /* The tile loader.  Stereo layouts: rows 2k and 2k+1 of the warp are the two channels of one
+     * frame (a warp's first subframe is even), so one load of the (left, right) pair at position p
+     * feeds both rows -- half the loads of reading two planes; everything inside is branch free so
+     * that the 16 x LD loads of a tile are in flight together while the previous tile is analysed.
+     * Other layouts take fb_pcm_sample per row. */
 #define FB_LPC_LOAD_TILE(tb)                                                              \
     do {                                                                                  \
-        _Pragma("unroll")                                                                 \
-        for (int r = 0; r < 16; r++) {                                                    \
-            const int32_t *rp = s_ptr[warp][r];                                           \
-            const int rn = s_n[warp][r], rh = s_hole[warp][r];                            \
+        if (LK == FB_LPC_LK_PLANES) {                                                     \
             _Pragma("unroll")                                                             \
-            for (int l = 0; l < G::LD; l++) {                                             \
-                const int p = (tb) + lane + 32 * l;                                       \
-                pre[r * G::LD + l] = (lane + 32 * l < G::TL && p < rn && p != rh) ? rp[p] : 0; \
+            for (int r = 0; r < 16; r++) {                                                \
+                const int32_t *rp = planes + (size_t)s_ebase[warp][r];                    \
+                const int rn = s_n[warp][r], rh = s_hole[warp][r];                        \
+                _Pragma("unroll")                                                         \
+                for (int l = 0; l < G::LD; l++) {                                         \
+                    const int p = (tb) + lane + 32 * l;                                   \
+                    pre[r * G::LD + l] = (lane + 32 * l < G::TL && p < rn && p != rh) ? rp[p] : 0; \
+                }                                                                         \
+            }                                                                             \
+        } else if (LK != FB_LPC_LK_GENERIC) {                                             \
+            _Pragma("unroll")                                                             \
+            for (int rp = 0; rp < 8; rp++) {                                              \
+                const size_t pe = (size_t)s_ebase[warp][2 * rp] >> 1;                     \
+                const int nf_ = s_nf[warp][2 * rp], rh = s_hole[warp][2 * rp];            \
+                const int n0_ = s_n[warp][2 * rp], n1_ = s_n[warp][2 * rp + 1];           \
+                const int c0_ = s_coef[warp][2 * rp], c1_ = s_coef[warp][2 * rp + 1];     \
+                _Pragma("unroll")                                                         \
+                for (int l = 0; l < G::LD; l++) {                                         \
+                    const int p = (tb) + lane + 32 * l;                                   \
+                    const bool ok = lane + 32 * l < G::TL && p < nf_ && p != rh;          \
+                    int32_t a_, b_;                                                       \
+                    if (LK == FB_LPC_LK_S16_STEREO) {                                     \
+                        const uint32_t w_ = ok ? reinterpret_cast<const uint32_t *>(pcm)[pe + (size_t)p] : 0u; \
+                        a_ = fb_stereo_apply16(c0_, w_); b_ = fb_stereo_apply16(c1_, w_); \
+                    } else {                                                              \
+                        const uint16_t *h_ = reinterpret_cast<const uint16_t *>(pcm) + 3 * (pe + (size_t)p); \
+                        const uint32_t h0 = ok ? h_[0] : 0u, h1 = ok ? h_[1] : 0u, h2 = ok ? h_[2] : 0u; \
+                        const int32_t lv = (int32_t)((h0 | (h1 << 16)) << 8) >> 8;        \
+                        const int32_t rv = (int32_t)(((h1 >> 8) | (h2 << 8)) << 8) >> 8;  \
+                        a_ = fb_stereo_apply(c0_, lv, rv); b_ = fb_stereo_apply(c1_, lv, rv); \
+                    }                                                                     \
+                    pre[(2 * rp) * G::LD + l] = p < n0_ ? a_ : 0;                         \
+                    pre[(2 * rp + 1) * G::LD + l] = p < n1_ ? b_ : 0;                     \
+                }                                                                         \
+            }                                                                             \
+        } else {                                                                          \
+            _Pragma("unroll")                                                             \
+            for (int r = 0; r < 16; r++) {                                                \
+                const size_t re = (size_t)s_ebase[warp][r];                               \
+                const int rn = s_n[warp][r], rh = s_hole[warp][r], rc = s_cmw[warp][r];   \
+                _Pragma("unroll")                                                         \
+                for (int l = 0; l < G::LD; l++) {                                         \
+                    const int p = (tb) + lane + 32 * l;                                   \
+                    pre[r * G::LD + l] = (lane + 32 * l < G::TL && p < rn && p != rh)     \
+                        ? fb_pcm_sample(pcm, fmt, re, C, rc & 0xff, (rc >> 8) & 0xff, rc >> 16, p) : 0; \
+                }                                                                         \
             }                                                                             \
         }                                                                                 \
     } while (0)

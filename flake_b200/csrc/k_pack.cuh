@@ -175,8 +175,8 @@ __device__ __forceinline__ FbSubLayout fb_sub_layout(const FbSub *sb, int n, boo
  * order), so every frame a CTA looks back at belongs to a CTA that is already running or done.
  */
 __global__ void __launch_bounds__(FB_PACK_THREADS)
-k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
-       const int32_t *res, FbSub *subs, const uint8_t *ch_modes, uint8_t *slots,
+k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const void *pcm, int fmt,
+       const int32_t *planes, const int32_t *res, FbSub *subs, const uint8_t *ch_modes, uint8_t *slots,
        uint32_t *frame_len, uint32_t *frame_bs, int smem_words,
        const uint16_t *xpow32, const uint32_t *crc16_tables,
        uint32_t *ticket, unsigned long long *status, uint64_t *frame_off, uint8_t *out, FbSummary *summary)
@@ -276,7 +276,7 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
             const FbSub *sb = &subs[(size_t)f * C + c];
             const FbSubLayout L = fb_sub_layout(sb, n, verbatim);
             const size_t off = (size_t)fr.start * C + (size_t)c * n;
-            const int32_t *data = (L.type == 1 || L.type == 0) ? smp + off : res + off;
+            const int32_t *data = res + off;             /* read for Rice-coded subframes only */
             const bool rice = (L.type == 8 || L.type == 32);
             const uint8_t *kp = s_params[c];
 
@@ -337,7 +337,7 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
         const FbSub *sb = &subs[(size_t)f * C + c];
         const FbSubLayout L = fb_sub_layout(sb, n, verbatim);
         const size_t off = (size_t)fr.start * C + (size_t)c * n;
-        const int32_t *data = (L.type == 1 || L.type == 0) ? smp + off : res + off;
+        const int32_t *data = res + off;                 /* warm-up samples and residuals of Rice-coded subframes */
         const bool rice = (L.type == 8 || L.type == 32);
         const uint8_t *kp = s_params[c];
         const uint64_t bitpos = chbit[c];
@@ -388,7 +388,12 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32
         if ((L.type == 1 && i0 < i1) || (rice && jbeg < i1)) {
             FbBitPut b; fb_bp_init(b, wbuf, capw, bitpos + L.preamble_bits + myoff[c]);
             if (L.type == 1) {
-                for (int i = i0; i < i1; i++) fb_bp_put_signed(b, L.obits, data[i]);
+                /* VERBATIM (optimize.c:154-158, 278-289): the transformed samples themselves, taken
+                 * from the packed PCM (mono, stereo) or from k_prep's planes (fb_uses_planes); rare */
+                const int mode = ch_modes[f];
+                for (int i = i0; i < i1; i++)
+                    fb_bp_put_signed(b, L.obits, fb_uses_planes(C) ? planes[off + (size_t)i]
+                                     : fb_pcm_sample(pcm, fmt, (size_t)fr.start * C, C, c, mode, L.wasted, i));
             } else {
                 int i = jbeg;
                 int p = i / L.psize;

@@ -4,11 +4,14 @@
  * estimate and transform (encode.c:598-694), wasted bits (encode.c:558-593),
  * CONSTANT detection (optimize.c:143-151).
  *
- * Data layout written here: for a frame starting at sample `start` with n
- * samples and C channels, channel c's plane is the int32 run
- *     smp[start*C + c*n .. start*C + (c+1)*n)
- * so the planes of a chunk tile the scratch buffer exactly like the
- * interleaved input does.
+ * k_prep reads the packed PCM through a TMA-filled shared-memory tile and writes
+ * decisions: the stereo mode per frame and, per subframe, wasted bits, sample width,
+ * the CONSTANT flag and the magnitude bound.  For mono and stereo input that is all:
+ * the consumers deinterleave and decorrelate the packed PCM themselves and no int32
+ * plane is kept in global memory.  With more than two channels a consumer of ONE
+ * channel would have to pull the whole interleaved frame through its shared memory
+ * (8 channels: eight times the bytes it needs), so there k_prep also deinterleaves
+ * into int32 planes, once, for k_lpc / k_search / k_pack to read (fb_uses_planes).
  */
 #ifndef FLAKE_B200_K_PREP_CUH
 #define FLAKE_B200_K_PREP_CUH
@@ -19,7 +22,7 @@
 #define FB_PREP_THREADS 128      /* with 12 CTAs per SM: 0.42 ms per C2 stream; 256 x 6: 0.48; 512 x 3: 0.70 */
 #endif
 #ifndef FB_PREP_MINBLOCKS
-#define FB_PREP_MINBLOCKS 12    /* <= 42 registers */
+#define FB_PREP_MINBLOCKS 8     /* <= 64 registers; 8 x 16 KB of tile staging per SM */
 #endif
 
 /* staging-slot geometry: frame f of a chunk gets a slot that is large enough
@@ -151,144 +154,115 @@ k_frames_vbs(FbConfig cfg, uint32_t nsamples, uint32_t first_number,
 }
 
 /* ------------------------------------------------------------------ */
-/* prepare: one CTA per frame                                           */
+/* prepare: one CTA per frame, READ-ONLY over the packed PCM             */
 /* ------------------------------------------------------------------ */
+/*
+ * One pass over the frame's packed PCM, staged through shared memory by TMA bulk copies
+ * (FbTile, dev_common.cuh).  Nothing is written back but the decisions: no int32 plane exists
+ * in global memory -- k_lpc, k_search and k_pack deinterleave and decorrelate the packed PCM
+ * themselves from the frame's stereo decision (encode.c:541-553, 648-694).
+ *
+ *   stereo: the four estimate sums of calc_decorr_scores (encode.c:598-643) and, because the
+ *           decision is not known yet, the statistics of all four candidate channels
+ *           (left, right, mid, side); the chosen pair's statistics become the subframe records;
+ *   other:  per-channel statistics.
+ * Statistics per plane: OR of all samples (`ctz(OR)` = wasted bits, encode.c:558-593),
+ * minimum and maximum (min == max is the CONSTANT test, optimize.c:143-151; max(|min|,|max|)
+ * bounds k_search's 32-bit arithmetic test).
+ */
 #define FB_PREP_RUN 8
 
-/* Samples i-2 .. i+7 of a stereo frame into lw[0..9] / rw[0..9] (index 2 = sample i);
- * positions outside [0, n) read as 0.  `ibase` = interleaved element index of the frame's
- * sample 0.  Whole in-range runs of packed s16 (two 16-byte loads) and int32 (four) are
- * loaded vectorised when the address allows. */
-__device__ __forceinline__ void fb_load_stereo_run(const void *pcm, int fmt, size_t ibase, int i, int n,
-                                                   int32_t *lw, int32_t *rw)
-{
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int idx = i - 2 + k;
-        const bool ok = idx >= 0 && idx < n;
-        lw[k] = ok ? fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)idx) : 0;
-        rw[k] = ok ? fb_load_pcm(pcm, fmt, ibase + 2 * (size_t)idx + 1) : 0;
-    }
-    const size_t e0 = ibase + 2 * (size_t)i;
-    if (i + FB_PREP_RUN <= n && fmt == FB_PCM_S16LE && ((((size_t)pcm) + e0 * 2) & 15u) == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>((const uint8_t *)pcm + e0 * 2);
-        const uint4 a = src[0], b = src[1];
-        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int k = 0; k < 8; k++) { lw[2 + k] = (int32_t)(w[k] << 16) >> 16; rw[2 + k] = (int32_t)w[k] >> 16; }
-    } else if (i + FB_PREP_RUN <= n && fmt == FB_PCM_S32 && ((((size_t)pcm) + e0 * 4) & 15u) == 0) {
-        const int4 *src = reinterpret_cast<const int4 *>((const uint8_t *)pcm + e0 * 4);
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const int4 v = src[g];
-            lw[2 + 2 * g] = v.x; rw[2 + 2 * g] = v.y; lw[3 + 2 * g] = v.z; rw[3 + 2 * g] = v.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < FB_PREP_RUN; k++) {
-            const bool ok = i + k < n;
-            lw[2 + k] = ok ? fb_load_pcm(pcm, fmt, e0 + 2 * (size_t)k) : 0;
-            rw[2 + k] = ok ? fb_load_pcm(pcm, fmt, e0 + 2 * (size_t)k + 1) : 0;
-        }
-    }
-}
-
-/* decorrelated pair (a, b) of a stereo sample, encode.c:648-694; MODE is the frame's ch_mode */
-template <int MODE>
-__device__ __forceinline__ void fb_decorrelate(int32_t l, int32_t r, int32_t &a, int32_t &b)
-{
-    if (MODE == 10)     { a = (int32_t)((uint32_t)l + (uint32_t)r) >> 1; b = (int32_t)((uint32_t)l - (uint32_t)r); }
-    else if (MODE == 8) { a = l; b = (int32_t)((uint32_t)l - (uint32_t)r); }
-    else if (MODE == 9) { a = (int32_t)((uint32_t)l - (uint32_t)r); b = r; }
-    else                { a = l; b = r; }
-}
-
-/* plane statistics of one channel: OR of all samples (wasted bits), minimum and maximum
- * (|sample| bound for k_search's 32-bit test; min == max is the CONSTANT test) */
 struct FbPlaneStat { uint32_t orv; int32_t mn, mx; };
 
-/* deinterleave + decorrelate a stereo frame in 8-sample runs, gather the statistics */
-template <int MODE>
-__device__ __forceinline__ void fb_prep_stereo(const void *pcm, int fmt, size_t ibase, int n, int32_t *plane,
-                                               FbPlaneStat &sa, FbPlaneStat &sb)
+__device__ __forceinline__ void fb_stat_add(FbPlaneStat &s, int32_t v)
 {
-    const int tid = threadIdx.x, T = blockDim.x;
-    const bool planes_aligned = ((((size_t)plane) | ((size_t)n * 4u)) & 15u) == 0;
-    for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
-        int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2], av[FB_PREP_RUN], bv[FB_PREP_RUN];
-        fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
-#pragma unroll
-        for (int k = 0; k < FB_PREP_RUN; k++) fb_decorrelate<MODE>(lw[k + 2], rw[k + 2], av[k], bv[k]);
-        if (i + FB_PREP_RUN <= n) {
-#pragma unroll
-            for (int k = 0; k < FB_PREP_RUN; k++) {
-                sa.orv |= (uint32_t)av[k]; sa.mn = min(sa.mn, av[k]); sa.mx = max(sa.mx, av[k]);
-                sb.orv |= (uint32_t)bv[k]; sb.mn = min(sb.mn, bv[k]); sb.mx = max(sb.mx, bv[k]);
-            }
-            if (planes_aligned) {
-                int4 *pa = reinterpret_cast<int4 *>(plane + i), *pb = reinterpret_cast<int4 *>(plane + n + i);
-                pa[0] = make_int4(av[0], av[1], av[2], av[3]); pa[1] = make_int4(av[4], av[5], av[6], av[7]);
-                pb[0] = make_int4(bv[0], bv[1], bv[2], bv[3]); pb[1] = make_int4(bv[4], bv[5], bv[6], bv[7]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < FB_PREP_RUN; k++) { plane[i + k] = av[k]; plane[n + i + k] = bv[k]; }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < FB_PREP_RUN; k++) {
-                if (i + k < n) {
-                    sa.orv |= (uint32_t)av[k]; sa.mn = min(sa.mn, av[k]); sa.mx = max(sa.mx, av[k]);
-                    sb.orv |= (uint32_t)bv[k]; sb.mn = min(sb.mn, bv[k]); sb.mx = max(sb.mx, bv[k]);
-                    plane[i + k] = av[k]; plane[n + i + k] = bv[k];
-                }
-            }
-        }
-    }
+    s.orv |= (uint32_t)v; s.mn = min(s.mn, v); s.mx = max(s.mx, v);
 }
 
 __global__ void __launch_bounds__(FB_PREP_THREADS, FB_PREP_MINBLOCKS)
-k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint32_t *nframes,
-       int32_t *smp, FbSub *subs, uint8_t *ch_modes)
+k_prep(FbConfig cfg, const void *pcm, int fmt, unsigned long long pcm_bytes, const FbFrame *frames,
+       const uint32_t *nframes, int32_t *planes, FbSub *subs, uint8_t *ch_modes)
 {
+    __shared__ __align__(16) uint8_t s_tile[FB_TILE_BYTES];
+    __shared__ fb_mbar_t s_bar[FB_TILE_STAGES];
+    __shared__ int32_t s_carry[2][4];                 /* last two (l, r) pairs of a chunk, by chunk parity */
     __shared__ uint64_t s_sum[FB_PREP_THREADS / 32][4];
     __shared__ uint32_t s_or[FB_PREP_THREADS / 32][FB_MAX_CH_UNROLL];
     __shared__ int32_t s_mn[FB_PREP_THREADS / 32][FB_MAX_CH_UNROLL], s_mx[FB_PREP_THREADS / 32][FB_MAX_CH_UNROLL];
-    __shared__ int s_mode;
     __shared__ int s_wasted[FB_MAX_CH_UNROLL];
     const uint32_t f = blockIdx.x;
     if (f >= *nframes) return;
     const FbFrame fr = frames[f];
     const int n = (int)fr.n, C = cfg.channels;
     const size_t ibase = (size_t)fr.start * (size_t)C;      /* interleaved index of sample 0 */
-    int32_t *plane = smp + ibase;
     const int tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nw = (T + 31) >> 5;
 
-    /* ---- stereo mode estimate, encode.c:598-643 ---------------------- */
-    int mode = 0;                                            /* NOT_STEREO */
-    if (C == 2) {
-        mode = 1;                                            /* LEFT_RIGHT */
-        if (n > 32 && cfg.stereo_method == 1) {
-            uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN) {
+    FbTile tile;
+    fb_tile_begin(tile, pcm, fmt, ibase, n, C, pcm_bytes, s_tile, s_bar);
+
+    /* planes 0..3 of a stereo frame: left, right, mid, side; else one per channel */
+    FbPlaneStat st[FB_MAX_CH_UNROLL];
+#pragma unroll
+    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) { st[c].orv = 0; st[c].mn = 0x7fffffff; st[c].mx = (int32_t)0x80000000; }
+    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    const bool estimate = C == 2 && n > 32 && cfg.stereo_method == 1;
+
+    for (uint32_t k = 0; k < tile.nchunks; k++) {
+        uint32_t nb;
+        const uint8_t *t = fb_tile_acquire(tile, k, &nb);
+        const int base = (int)(k * tile.chunk_samples);               /* first sample of the chunk */
+        const int cs = min((int)tile.chunk_samples, n - base);        /* samples in the chunk */
+        if (C == 2) {
+            for (int q = tid * FB_PREP_RUN; q < cs; q += T * FB_PREP_RUN) {
+                /* lw[2 + j] = sample base + q + j; lw[0], lw[1] = the two before it */
                 int32_t lw[FB_PREP_RUN + 2], rw[FB_PREP_RUN + 2];
-                fb_load_stereo_run(pcm, fmt, ibase, i, n, lw, rw);
+                if (q + FB_PREP_RUN <= cs) {
+                    fb_tile_stereo4(t, fmt, (uint32_t)q, lw + 2, rw + 2);
+                    fb_tile_stereo4(t, fmt, (uint32_t)q + 4u, lw + 6, rw + 6);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < FB_PREP_RUN; j++) {
+                        const bool ok = q + j < cs;
+                        lw[2 + j] = ok ? fb_tile_elem(t, fmt, 2u * (uint32_t)(q + j)) : 0;
+                        rw[2 + j] = ok ? fb_tile_elem(t, fmt, 2u * (uint32_t)(q + j) + 1u) : 0;
+                    }
+                }
+                if (q >= 2) {
+                    lw[0] = fb_tile_elem(t, fmt, 2u * (uint32_t)(q - 2)); rw[0] = fb_tile_elem(t, fmt, 2u * (uint32_t)(q - 2) + 1u);
+                    lw[1] = fb_tile_elem(t, fmt, 2u * (uint32_t)(q - 1)); rw[1] = fb_tile_elem(t, fmt, 2u * (uint32_t)(q - 1) + 1u);
+                } else {                                              /* q == 0: the previous chunk's tail */
+                    lw[0] = k ? s_carry[(k - 1) & 1][0] : 0; rw[0] = k ? s_carry[(k - 1) & 1][1] : 0;
+                    lw[1] = k ? s_carry[(k - 1) & 1][2] : 0; rw[1] = k ? s_carry[(k - 1) & 1][3] : 0;
+                }
+                if (q + FB_PREP_RUN == cs) {                          /* the last run of a chunk leaves the carry (a chunk
+                                                                       * that is followed by another one is whole runs) */
+                    s_carry[k & 1][0] = lw[FB_PREP_RUN]; s_carry[k & 1][1] = rw[FB_PREP_RUN];
+                    s_carry[k & 1][2] = lw[FB_PREP_RUN + 1]; s_carry[k & 1][3] = rw[FB_PREP_RUN + 1];
+                }
                 /* 32-bit sums inside a run: 8 terms below 2^28 each when the packed format bounds
                  * the samples to 24 bits; int32 input may hold anything and is summed in 64 bits */
                 uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-                const bool whole = i >= 2 && i + FB_PREP_RUN <= n;
 #pragma unroll
-                for (int k = 0; k < FB_PREP_RUN; k++) {
-                    if (!whole && (i + k < 2 || i + k >= n)) continue;
-                    const int32_t lt = (int32_t)((uint32_t)lw[k + 2] - 2u * (uint32_t)lw[k + 1] + (uint32_t)lw[k]);
-                    const int32_t rt = (int32_t)((uint32_t)rw[k + 2] - 2u * (uint32_t)rw[k + 1] + (uint32_t)rw[k]);
+                for (int j = 0; j < FB_PREP_RUN; j++) {
+                    if (q + j >= cs) continue;
+                    const int32_t l = lw[j + 2], r = rw[j + 2];
+                    fb_stat_add(st[0], l);
+                    fb_stat_add(st[1], r);
+                    fb_stat_add(st[2], (int32_t)((uint32_t)l + (uint32_t)r) >> 1);
+                    fb_stat_add(st[3], (int32_t)((uint32_t)l - (uint32_t)r));
+                    if (!estimate || base + q + j < 2) continue;
+                    const int32_t lt = (int32_t)((uint32_t)l - 2u * (uint32_t)lw[j + 1] + (uint32_t)lw[j]);
+                    const int32_t rt = (int32_t)((uint32_t)r - 2u * (uint32_t)rw[j + 1] + (uint32_t)rw[j]);
                     const int32_t m = (int32_t)((uint32_t)lt + (uint32_t)rt) >> 1;
                     const int32_t d = (int32_t)((uint32_t)lt - (uint32_t)rt);
                     if (fmt != FB_PCM_S32) {
-                        a0 += (uint32_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
-                        a1 += (uint32_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
-                        a2 += (uint32_t)(m < 0 ? (int32_t)(0u - (uint32_t)m) : m);
-                        a3 += (uint32_t)(d < 0 ? (int32_t)(0u - (uint32_t)d) : d);
+                        /* |x| + acc in one instruction (VABSDIFF); lt, rt stay below 2^26 for packed
+                         * input, so |lt - rt| needs no wrap-around */
+                        a0 = __sad(lt, 0, a0);
+                        a1 = __sad(rt, 0, a1);
+                        a2 = __sad(m, 0, a2);
+                        a3 = __sad(lt, rt, a3);
                     } else {
                         s0 += (uint64_t)(int64_t)(lt < 0 ? (int32_t)(0u - (uint32_t)lt) : lt);
                         s1 += (uint64_t)(int64_t)(rt < 0 ? (int32_t)(0u - (uint32_t)rt) : rt);
@@ -298,57 +272,32 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
                 }
                 s0 += a0; s1 += a1; s2 += a2; s3 += a3;
             }
-            s0 = fb_warp_sum_u64(s0); s1 = fb_warp_sum_u64(s1); s2 = fb_warp_sum_u64(s2); s3 = fb_warp_sum_u64(s3);
-            if (lane == 0) { s_sum[warp][0] = s0; s_sum[warp][1] = s1; s_sum[warp][2] = s2; s_sum[warp][3] = s3; }
-            __syncthreads();
-            if (tid == 0) {
-                uint64_t s[4] = {0, 0, 0, 0}, score[4];
-                for (int w = 0; w < nw; w++)
-                    for (int q = 0; q < 4; q++) s[q] += s_sum[w][q];
-                for (int i = 0; i < 4; i++) {
-                    /* k from the uint32-truncated search, cost kept in uint64 (encode.c:617-620) */
-                    const uint64_t two = 2 * s[i];
-                    const int best = fb_rice_k(two, n);
-                    s[i] = fb_rice_count64(two, n, best);
-                }
-                score[0] = s[0] + s[1]; score[1] = s[0] + s[3];
-                score[2] = s[1] + s[3]; score[3] = s[2] + s[3];
-                int best = 0;
-                for (int i = 1; i < 4; i++) if (score[i] < score[best]) best = i;
-                s_mode = best == 0 ? 1 : (best == 1 ? 8 : (best == 2 ? 9 : 10));
-            }
-            __syncthreads();
-            mode = s_mode;
-        }
-    }
-
-    /* ---- deinterleave + decorrelate, gather plane statistics ----------- */
-    FbPlaneStat st[FB_MAX_CH_UNROLL];
+        } else {
+            /* deinterleave (encode.c:541-553): channel c of the frame is the plane
+             * [ibase + c n, + n); consecutive threads write consecutive words of a plane */
+            const bool to_planes = fb_uses_planes(C);
+            for (int q = tid; q < cs; q += T) {
 #pragma unroll
-    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) { st[c].orv = 0; st[c].mn = 0x7fffffff; st[c].mx = (int32_t)0x80000000; }
-
-    if (C == 2) {
-        if (mode == 10)     fb_prep_stereo<10>(pcm, fmt, ibase, n, plane, st[0], st[1]);
-        else if (mode == 8) fb_prep_stereo<8>(pcm, fmt, ibase, n, plane, st[0], st[1]);
-        else if (mode == 9) fb_prep_stereo<9>(pcm, fmt, ibase, n, plane, st[0], st[1]);
-        else                fb_prep_stereo<1>(pcm, fmt, ibase, n, plane, st[0], st[1]);
-    } else {
-        for (int i = tid; i < n; i += T) {
-#pragma unroll
-            for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
-                if (c < C) {
-                    const int32_t a = fb_load_pcm(pcm, fmt, ibase + (size_t)i * C + c);
-                    plane[(size_t)c * n + i] = a;
-                    st[c].orv |= (uint32_t)a; st[c].mn = min(st[c].mn, a); st[c].mx = max(st[c].mx, a);
-                }
+                for (int c = 0; c < FB_MAX_CH_UNROLL; c++)
+                    if (c < C) {
+                        const int32_t v = fb_tile_elem(t, fmt, (uint32_t)q * (uint32_t)C + (uint32_t)c);
+                        fb_stat_add(st[c], v);
+                        if (to_planes) planes[ibase + (size_t)c * (size_t)n + (size_t)(base + q)] = v;
+                    }
             }
         }
+        fb_tile_release(tile, k);
     }
 
-    /* ---- wasted bits (encode.c:558-593) + subframe records -------------- */
+    /* ---- reductions ------------------------------------------------------------------ */
+    if (estimate) {
+        s0 = fb_warp_sum_u64(s0); s1 = fb_warp_sum_u64(s1); s2 = fb_warp_sum_u64(s2); s3 = fb_warp_sum_u64(s3);
+        if (lane == 0) { s_sum[warp][0] = s0; s_sum[warp][1] = s1; s_sum[warp][2] = s2; s_sum[warp][3] = s3; }
+    }
+    const int nplanes = C == 2 ? 4 : C;
 #pragma unroll
     for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
-        if (c < C) {
+        if (c < nplanes) {
             const uint32_t o = __reduce_or_sync(FB_FULL_MASK, st[c].orv);
             const int32_t lo = __reduce_min_sync(FB_FULL_MASK, st[c].mn);
             const int32_t hi = __reduce_max_sync(FB_FULL_MASK, st[c].mx);
@@ -356,17 +305,43 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
         }
     }
     __syncthreads();
+
+    /* ---- stereo mode, encode.c:598-643 (every thread of warp 0 computes the same) ----- */
+    int mode = 0;                                            /* NOT_STEREO */
+    if (C == 2) {
+        mode = 1;                                            /* LEFT_RIGHT */
+        if (estimate) {
+            uint64_t s[4] = {0, 0, 0, 0}, score[4];
+            for (int w = 0; w < nw; w++)
+                for (int q = 0; q < 4; q++) s[q] += s_sum[w][q];
+            for (int i = 0; i < 4; i++) {
+                /* k from the uint32-truncated search, cost kept in uint64 (encode.c:617-620) */
+                const uint64_t two = 2 * s[i];
+                const int best = fb_rice_k(two, n);
+                s[i] = fb_rice_count64(two, n, best);
+            }
+            score[0] = s[0] + s[1]; score[1] = s[0] + s[3];
+            score[2] = s[1] + s[3]; score[3] = s[2] + s[3];
+            int best = 0;
+            for (int i = 1; i < 4; i++) if (score[i] < score[best]) best = i;
+            mode = best == 0 ? 1 : (best == 1 ? 8 : (best == 2 ? 9 : 10));
+        }
+    }
+
+    /* ---- wasted bits (encode.c:558-593) + subframe records ---------------------------- */
     if (tid < C) {
         const int c = tid;
+        /* the plane this channel carries after decorrelation */
+        int pl = c;
+        if (C == 2) pl = c == 0 ? (mode == 10 ? 2 : (mode == 9 ? 3 : 0)) : ((mode == 1 || mode == 9) ? 1 : 3);
         uint32_t o = 0;
         int32_t lo = 0x7fffffff, hi = (int32_t)0x80000000;
-        for (int w = 0; w < nw; w++) { o |= s_or[w][c]; lo = min(lo, s_mn[w][c]); hi = max(hi, s_mx[w][c]); }
+        for (int w = 0; w < nw; w++) { o |= s_or[w][pl]; lo = min(lo, s_mn[w][pl]); hi = max(hi, s_mx[w][pl]); }
         int wasted = 0;
         if (o) {
             wasted = __ffs((int)o) - 1;
             if (wasted >= cfg.bps - 1) wasted = 0;
         }
-        s_wasted[c] = wasted;
         /* bound on |sample|: ~v for negative v (two's complement magnitude - 1) */
         const uint32_t m = max((uint32_t)(hi < 0 ? ~hi : hi), (uint32_t)(lo < 0 ? ~lo : lo));
         FbSub *sb = &subs[(size_t)f * C + c];
@@ -380,22 +355,19 @@ k_prep(FbConfig cfg, const void *pcm, int fmt, const FbFrame *frames, const uint
         sb->maxabs = (m >> wasted) + 1u;
         sb->type = -1; sb->order = 0; sb->shift = 0; sb->method = 0; sb->porder = 0;
         sb->est_order = 0; sb->est_bits = 0;
+        s_wasted[c] = wasted;
     }
     if (tid == 0) ch_modes[f] = (uint8_t)mode;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < FB_MAX_CH_UNROLL; c++) {
-        if (c < C) {
-            const int wasted = s_wasted[c];
-            if (wasted) {
-                int32_t *pl = plane + (size_t)c * n;
-                if (C == 2) {                                       /* own elements only: same runs as above */
-                    for (int i = tid * FB_PREP_RUN; i < n; i += T * FB_PREP_RUN)
-                        for (int k = 0; k < FB_PREP_RUN && i + k < n; k++) pl[i + k] >>= wasted;
-                } else {
-                    for (int i = tid; i < n; i += T) pl[i] >>= wasted;
-                }
-            }
+    /* planes hold the samples the subframe codes: wasted bits shifted out (encode.c:586-590).
+     * Rare, so a second walk over the few planes concerned (still in L2) instead of a shift in
+     * every consumer. */
+    if (fb_uses_planes(C)) {
+        __syncthreads();
+        for (int c = 0; c < C; c++) {
+            const int w = s_wasted[c];
+            if (w == 0) continue;                           /* CTA-uniform */
+            int32_t *pl = planes + ibase + (size_t)c * (size_t)n;
+            for (int i = tid; i < n; i += T) pl[i] >>= w;
         }
     }
 }

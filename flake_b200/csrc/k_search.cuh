@@ -29,6 +29,7 @@
 
 #include "dev_common.cuh"
 #include "k_lpc.cuh"
+#include <type_traits>
 
 #ifndef FB_SEARCH_THREADS
 #define FB_SEARCH_THREADS 128    /* 16 samples per thread and tile; measured best of 64/96/128/256 on B200 */
@@ -65,6 +66,7 @@ struct FbSearchShared {
     uint32_t sumabs[MAXP];          /* sum |coef| per row */
     uint8_t  narrow_of[MAXP];       /* row can be costed in 32-bit arithmetic */
     uint8_t  pmin_of[MAXP + 1], pmax_of[MAXP + 1];   /* partition-order limits per predictor order (rice.c:148-171) */
+    uint8_t  sum32_of[MAXP];        /* every partition sum of the row's residual is below 2^31 (32-bit pyramid) */
     uint32_t result[FB_GROUP_MAX];      /* of the group members just finished */
     int32_t  porder[FB_GROUP_MAX], method[FB_GROUP_MAX];
     int32_t  best_porder, best_method;
@@ -211,7 +213,8 @@ __device__ __noinline__ void fb_finish_wide(FbSearchShared<MAXP> &S, int slot, c
 }
 
 /*
- * One whole warp.  When every entry of F is below 2^31 / entries, every partition sum of every
+ * One whole warp.  When the block's zig-zag total is provably below 2^31 (S.sum32_of, from the
+ * magnitude bound of the plane and the row's coefficients), every partition sum of every
  * level is below 2^31 and the whole finish is exact in 32-bit arithmetic (the costs are uint32
  * in the reference, rice.c:30-45, and `sum - n/2` can only wrap where k = 0, where the wrap is
  * the same modulo 2^32); otherwise the 64-bit body.
@@ -220,12 +223,9 @@ template <int MAXP>
 __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, const unsigned long long *F,
                                             int per, int n, int is_lpc, int order, int obits, int pmin, int pmax)
 {
-    const int nent = per << pmax;                                   /* entries of F, <= 4096 */
-    const int rs = 31 - (32 - __clz(nent - 1 | 1));                 /* entries < 2^rs  =>  total < 2^31 */
-    unsigned long long hi = 0;
-#pragma unroll 4
-    for (int q = threadIdx.x & 31; q < nent; q += 32) hi |= F[q] >> rs;
-    if (__any_sync(FB_FULL_MASK, hi != 0)) {
+    /* S.sum32_of: 2 * (bound on |residual|) * n < 2^31 was proven when the row was staged (a scan
+     * of the run sums here instead: 3.24 vs 3.16 ms) */
+    if (!S.sum32_of[is_lpc ? order - 1 : order]) {
         fb_finish_wide<MAXP>(S, slot, F, per, n, is_lpc, order, obits, pmin, pmax);
         return;
     }
@@ -326,11 +326,16 @@ __host__ __device__ __forceinline__ int fb_skew(int logical) { return logical + 
 #else
 __host__ __device__ __forceinline__ int fb_skew(int logical) { return logical + ((logical >> 5) << 2); }
 #endif
-__host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n + FB_HIST + 16) + 8 + 1) & ~1; }
+__host__ __device__ __forceinline__ int fb_skew_words(int n) { return (fb_skew(n + FB_HIST + 16) + 8 + 3) & ~3; }
 /* 64-bit zig-zag sums, one per 16-sample run, per group member: words */
 __host__ __device__ __forceinline__ int fb_runsum_words(int n) { return 2 * (((n + FB_RUN - 1) / FB_RUN) + 2); }
-/* staged plane + the run sums of a whole group, in 32-bit words */
-__host__ __device__ __forceinline__ int fb_search_smem_words(int n, int group) { return fb_skew_words(n) + group * fb_runsum_words(n); }
+/* staged plane + (the run sums of a whole group | the TMA tile ring the plane is unpacked from: the
+ * ring is dead once the plane is staged, the run sums are only written after that), in 32-bit words */
+__host__ __device__ __forceinline__ int fb_search_smem_words(int n, int group)
+{
+    const int rs = group * fb_runsum_words(n), tile = FB_TILE_BYTES / 4;
+    return fb_skew_words(n) + (rs > tile ? rs : tile);
+}
 /* word offset of logical (16 m + d) relative to that of logical 16 m; d may be negative */
 __host__ __device__ constexpr int fb_skew_delta(int d) { return d + 4 * (d >= 0 ? d / 16 : -((-d + 15) / 16)); }
 
@@ -610,29 +615,30 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
                 c[4 * g] = v.x; c[4 * g + 1] = v.y; c[4 * g + 2] = v.z; c[4 * g + 3] = v.w;
             }
             const int shift = S.shift[row];
-            const int wlim = order - i0;                          /* samples of this run below the order */
             unsigned long long acc = 0;
             uint32_t a32 = 0;
+            const int wlim = order - i0;                          /* samples of this run below the order */
 #pragma unroll
             for (int k = 0; k < FB_RUN; k++) {
-                int32_t rk;
                 if (WIDE) {
                     long long pred = 0;
 #pragma unroll
                     for (int j = 0; j < P; j++) pred += (long long)c[j] * (long long)w[P + k - 1 - j];
-                    rk = (int32_t)((long long)w[P + k] - (pred >> shift));
+                    const int32_t rk = (int32_t)((long long)w[P + k] - (pred >> shift));
                     acc += fb_zigzag(rk);
+                    if (k < P && k < wlim) acc -= fb_zigzag(rk);       /* warm-up samples are not counted */
                 } else {
                     int32_t pred = 0;
 #pragma unroll
                     for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
-                    rk = w[P + k] - (pred >> shift);
                     /* zigzag(r) = (|4r + 1| - 1) / 2, |r| < 2^26: the sum of sixteen |4r + 1| fits 32 bits;
-                     * a warm-up sample (order <= P) counts as r = 0 */
+                     * |x| + acc is one instruction (VABSDIFF); a warm-up sample (order <= P) counts as r = 0.
+                     * (Measured and dropped: the warm-up runs costed apart by sixteen threads per run so
+                     * that this body does not know the case, 3.58 vs 3.16 ms.) */
+                    int32_t rk = w[P + k] - (pred >> shift);
                     if (k < P && k < wlim) rk = 0;
-                    a32 += (uint32_t)abs(4 * rk + 1);
+                    a32 = __sad(4 * rk + 1, 0, a32);
                 }
-                if (WIDE && k < P && k < wlim) acc -= fb_zigzag(rk);   /* warm-up samples are not counted */
             }
             runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)((a32 - FB_RUN) >> 1);
         }
@@ -749,11 +755,14 @@ __device__ __forceinline__ void fb_store_residual(FbSearchShared<MAXP> &S, const
 
 template <int MAXP>
 __global__ void __launch_bounds__(FB_SEARCH_THREADS, (MAXP > 12 ? FB_SEARCH_MINBLOCKS_WIDE : FB_SEARCH_MINBLOCKS))
-k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int32_t *smp,
-         int32_t *res, FbSub *subs, const int32_t *coefs, const int32_t *shifts, int smem_ints)
+k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const void *pcm, int fmt,
+         unsigned long long pcm_bytes, const uint8_t *ch_modes, int32_t *plane_scratch,
+         int32_t *res, FbSub *subs, const int32_t *coefs, const int32_t *shifts, const FbPlanNode *plan,
+         int smem_ints)
 {
     FB_DYN_SMEM(dyn);
     __shared__ __align__(16) FbSearchShared<MAXP> S;
+    __shared__ fb_mbar_t s_bar[FB_TILE_STAGES];
 
     const int C = cfg.channels;
     const uint32_t sf = blockIdx.x;
@@ -764,14 +773,15 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
     FbSub *sb = &subs[sf];
     const uint32_t nf = *nframes;
     const FbFrame fr = frames[f];
-    const int sb_obits = sb->obits, sb_const = sb->is_const;
+    const int sb_obits = sb->obits, sb_const = sb->is_const, sb_wasted = sb->wasted;
     const uint32_t sb_maxabs = sb->maxabs;
+    const int mode = ch_modes[f];
     if (f >= nf) return;
     const int n = (int)fr.n;
     const int tid = threadIdx.x, T = blockDim.x;
     FB_PROF_DECL;
-    const size_t off = (size_t)fr.start * C + (size_t)c * n;
-    const int32_t *xg = smp + off;
+    const size_t ebase = (size_t)fr.start * C;               /* interleaved element index of the frame's sample 0 */
+    const size_t off = ebase + (size_t)c * n;
     int32_t *rg = res + off;
     const int obits = sb_obits;
 
@@ -786,19 +796,30 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         return;
     }
 
-    /* stage the plane: skewed layout, FB_HIST zero samples in front (fast path) */
+    /*
+     * Stage the subframe's plane.  Mono / stereo: the frame's packed PCM comes in through the TMA
+     * tile ring (cp.async.bulk + mbarrier, two chunks in flight) and is deinterleaved, decorrelated
+     * by the frame's stereo decision and shifted by the wasted bits on its way into the skewed
+     * int32 layout (FB_HIST zero samples in front) that the run bodies read with 128-bit loads
+     * (encode.c:541-553, 648-694, 558-593 fused into the load).  More channels: k_prep's int32
+     * plane of this channel, asynchronous 16-byte copies straight into place.
+     */
     const bool fast = fb_search_smem_words(n, FB_GROUP_OF(MAXP)) <= smem_ints;
+    const bool from_planes = fb_uses_planes(C);
     int32_t *xs = (int32_t *)dyn;
-    if (fast) {
+    const int32_t *xg = from_planes ? plane_scratch + off : nullptr;
+    FbTile tile;
+    if (fast && !from_planes)                                 /* the frame's PCM is requested first ... */
+        fb_tile_begin(tile, pcm, fmt, ebase, n, C, pcm_bytes, (uint8_t *)(xs + fb_skew_words(n)), s_bar);
+    if (fast && from_planes) {
         for (int L = tid; L < FB_HIST; L += T) xs[fb_skew(L)] = 0;
         const int n4 = (((size_t)xg) & 15u) == 0 ? (n & ~3) : 0;
-        /* 16-byte groups never straddle a skew pad: asynchronous copies straight into place */
+        /* 16-byte groups never straddle a skew pad */
         for (int i = 4 * tid; i < n4; i += 4 * T) fb_cp_async16(xs + fb_skew(i + FB_HIST), xg + i);
 #pragma unroll 8
         for (int i = n4 + tid; i < n; i += T) xs[fb_skew(i + FB_HIST)] = xg[i];
         for (int i = n + tid; i < n + 16; i += T) xs[fb_skew(i + FB_HIST)] = 0;
     }
-
     int min_order = cfg.min_order, max_order = cfg.max_order;
     const bool fixed = (cfg.prediction_type == 1 || n <= max_order);
 
@@ -821,8 +842,9 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             for (int j = 0; j < MAXP; j++) S.coef[tid][j] = j < 4 ? bc[tid][j] : 0;   /* bodies may cover more taps */
             S.shift[tid] = 0;
             S.sumabs[tid] = sa[tid];
-            S.narrow_of[tid] = (unsigned long long)sa[tid] * sb_maxabs < 0x80000000ull &&
-                               ((unsigned long long)sb_maxabs + (unsigned long long)sa[tid] * sb_maxabs + 1ull) < (1ull << 26);
+            const unsigned long long rb = (unsigned long long)sb_maxabs + (unsigned long long)sa[tid] * sb_maxabs + 1ull;
+            S.narrow_of[tid] = (unsigned long long)sa[tid] * sb_maxabs < 0x80000000ull && rb < (1ull << 26);
+            S.sum32_of[tid] = 2ull * rb * (unsigned long long)n < 0x80000000ull;
         }
     } else {
         const int32_t *co = coefs + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
@@ -837,7 +859,65 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
         S.pmin_of[o] = (uint8_t)fb_limit_porder(cfg.min_porder, n, o);
         S.pmax_of[o] = (uint8_t)fb_limit_porder(cfg.max_porder, n, o);
     }
-    if (fast) fb_cp_async_wait_all();
+    /* ... and unpacked after the candidate rows have been requested, so that both latencies overlap */
+    if (fast && from_planes) {
+        fb_cp_async_wait_all();
+    } else if (fast) {
+        for (int L = tid; L < FB_HIST; L += T) xs[fb_skew(L)] = 0;
+        for (int i = ((n + 3) & ~3) + tid; i < n + 16; i += T) xs[fb_skew(i + FB_HIST)] = 0;
+        for (uint32_t k = 0; k < tile.nchunks; k++) {
+            uint32_t nb;
+            const uint8_t *t = fb_tile_acquire(tile, k, &nb);
+            const int base = (int)(k * tile.chunk_samples);
+            const int cs = min((int)tile.chunk_samples, n - base);
+            const int cs4 = cs & ~3;                                  /* whole groups of four samples */
+            const int coef = C == 2 ? fb_stereo_coef(mode, c, sb_wasted) : 0;
+            int32_t *dst = xs + fb_skew(base + FB_HIST);               /* base is a multiple of 16 */
+            if (C == 2 && fmt == FB_PCM_S16LE) {
+                /* a 128-bit load brings four (left, right) pairs; one dp2a + one shift per sample */
+                for (int q = 4 * tid; q < cs4; q += 4 * T) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(t + 4 * q);
+                    *reinterpret_cast<int4 *>(dst + fb_skew(q)) =
+                        make_int4(fb_stereo_apply16(coef, w.x), fb_stereo_apply16(coef, w.y),
+                                  fb_stereo_apply16(coef, w.z), fb_stereo_apply16(coef, w.w));
+                }
+            } else if (C == 2) {
+                for (int q = 4 * tid; q < cs4; q += 4 * T) {
+                    int32_t l[4], r[4];
+                    fb_tile_stereo4(t, fmt, (uint32_t)q, l, r);
+                    *reinterpret_cast<int4 *>(dst + fb_skew(q)) =
+                        make_int4(fb_stereo_apply(coef, l[0], r[0]), fb_stereo_apply(coef, l[1], r[1]),
+                                  fb_stereo_apply(coef, l[2], r[2]), fb_stereo_apply(coef, l[3], r[3]));
+                }
+            } else {
+                for (int q = 4 * tid; q < cs4; q += 4 * T) {
+                    int32_t v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = fb_tile_elem(t, fmt, (uint32_t)(q + j) * (uint32_t)C + (uint32_t)c) >> sb_wasted;
+                    *reinterpret_cast<int4 *>(dst + fb_skew(q)) = make_int4(v[0], v[1], v[2], v[3]);
+                }
+            }
+            /* the last one to three samples of the block; the rest of their group is zero */
+            if (tid < 4 && cs4 < cs) {
+                const int q = cs4 + tid;
+                int32_t v = 0;
+                if (q < cs) {
+                    if (C == 2) v = fb_stereo_apply(coef, fb_tile_elem(t, fmt, 2u * (uint32_t)q), fb_tile_elem(t, fmt, 2u * (uint32_t)q + 1u));
+                    else v = fb_tile_elem(t, fmt, (uint32_t)q * (uint32_t)C + (uint32_t)c) >> sb_wasted;
+                }
+                dst[fb_skew(q)] = v;
+            }
+            fb_tile_release(tile, k, false);     /* chunks land in disjoint parts of the plane */
+        }
+    } else if (!from_planes) {
+        /* blocks too large for shared memory (correctness path): the plane is materialised in a
+         * global scratch by this CTA and read back through generic pointers */
+        int32_t *pl = plane_scratch + off;
+        for (int i = tid; i < n; i += T) pl[i] = fb_pcm_sample(pcm, fmt, ebase, C, c, mode, sb_wasted, i);
+        xg = pl; X.xg = pl;
+        __syncthreads();
+    }
+
     __syncthreads();
     if (!fixed) {
         /* sum |c| per row from the staged rows (a loop of dependent global loads here cost more
@@ -848,8 +928,9 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             for (int j = 0; j < MAXP; j++) { const int32_t v = S.coef[rowi][j]; sa += (uint32_t)(v < 0 ? -v : v); }
             S.sumabs[rowi] = sa;                                    /* <= 32 * 16383 */
             const unsigned long long pm = (unsigned long long)sa * (unsigned long long)sb_maxabs;
-            S.narrow_of[rowi] = pm < 0x80000000ull &&
-                                ((unsigned long long)sb_maxabs + (pm >> S.shift[rowi]) + 1ull) < (1ull << 26);
+            const unsigned long long rb = (unsigned long long)sb_maxabs + (pm >> S.shift[rowi]) + 1ull;   /* bound on |residual| */
+            S.narrow_of[rowi] = pm < 0x80000000ull && rb < (1ull << 26);
+            S.sum32_of[rowi] = 2ull * rb * (unsigned long long)n < 0x80000000ull;   /* zig-zag <= 2 rb: every partition sum < 2^31 */
         }
         __syncthreads();
     }
@@ -932,35 +1013,19 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
             if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);
         }
     } else {
-        /* log search, optimize.c:241-261.  A step's candidates are last-step, last, last+step.
-         * Steps are merged into one group while the candidate set of the next step does not
-         * depend on the pending results (it is the same for every order that could be `last`
-         * by then); the steps are then replayed on the stored totals. */
+        /* log search, optimize.c:241-261.  A step's candidates are last-step, last, last+step; which
+         * orders are costed next depends only on the decisions so far, so the decision tree comes
+         * tabulated from the host (FbPlanNode, engine.h): cost the node's group, replay its steps on
+         * the totals exactly as the reference runs them, follow the child of the winner. */
         uint32_t done = 0;
         const int lo = min_order - 1, hi = max_order - 1;
-        opt_order = lo + (max_order - min_order) / 3;
+        uint32_t node = 0;
+        opt_order = (int)plan[0].start_order;
         int step = 16;
-        while (step > 0) {
-            int cnt = 0, nsteps = 0;
-            ord = 0;
-            uint32_t gmask = 0, hyp = 1u << opt_order;
-            const int lane = tid & 31;
-            const uint32_t range = (hi >= 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-            for (int s = step; s > 0; s >>= 1) {
-                /* lane h plays hypothesis `last == h`: its candidates {h-s, h, h+s} inside the
-                 * order range and not yet costed; the step joins the group when all live
-                 * hypotheses agree (OR == AND over them) */
-                const bool live = (hyp >> lane) & 1u;
-                uint32_t cm = 1u << lane;
-                if (lane - s >= 0) cm |= 1u << (lane - s);
-                if (lane + s < 32) cm |= 1u << (lane + s);
-                cm &= range & ~(done | gmask);
-                const uint32_t cor = __reduce_or_sync(FB_FULL_MASK, live ? cm : 0u);
-                const uint32_t cand = __reduce_and_sync(FB_FULL_MASK, live ? cm : 0xffffffffu);
-                if (cor != cand || cnt + __popc(cor) > FB_GROUP_OF(MAXP)) break;
-                for (uint32_t m = cor; m; m &= m - 1) { ord = fb_order_put(ord, cnt, __ffs((int)m)); cnt++; }
-                gmask |= cor; hyp |= cor; nsteps++;
-            }
+        while (node != FB_PLAN_END) {
+            const FbPlanNode nd = plan[node];
+            const int cnt = (int)nd.cnt, nsteps = (int)nd.nsteps;
+            ord = nd.ord;
             FB_PROF(5);
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             int bs = -1;
@@ -976,6 +1041,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const int
                 }
             }
             if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);
+            node = nd.child[bs + 1];
             FB_PROF(6);
         }
     }

@@ -271,6 +271,15 @@ inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)
 {
     sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 }
+inline unsigned __sad(int a, int b, unsigned c)
+{
+    const long long d = (long long)a - (long long)b;
+    return c + (unsigned)(d < 0 ? -d : d);
+}
+inline int __dp2a_lo(int a, int b, int c)
+{
+    return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)(b & 0xff) + (int)(int16_t)((unsigned)a >> 16) * (int)(int8_t)((b >> 8) & 0xff);
+}
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 inline int __mulhi(int a, int b) { return (int)(((int64_t)a * b) >> 32); }
 template <class T> inline T __ldg(const T *p) { return *p; }

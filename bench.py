@@ -13,16 +13,22 @@ rank encodes its own stream: frames shard with no collective, weak scaling).
   value   MSamples/s, KERNELS ONLY: PCM already resident in HBM (packed s16le, the
           WAV data layout), device-resident outputs, CUDA events on the launching
           stream, max over ranks.  No H2D/D2H, no MD5.
-  e2e     the like-for-like figure against the reference arm: the same metric through
-          the host-buffer C ABI (flake_b200_encode_stream on int32 samples -- the
-          flake_encode_frame convention): H2D, kernels, D2H, the MD5 of the PCM and the
-          final STREAMINFO all inside the timed region.
-  parity  the e2e output byte-compared with the compiled reference over the WHOLE
-          stream: frames compared / mismatching, compressed size delta.
+  e2e     the like-for-like figure against the reference arm, through the host-buffer
+          C ABI with BOTH arms free to use every host core: a FIXED corpus of independent
+          tracks (C5's shape: E2E_TRACKS x E2E_TRACK_SECONDS of flake -8 16-bit stereo,
+          packed s16le in page-locked host memory = the WAV data layout) through
+          flake_b200_encode_corpus -- H2D, kernels, D2H of frames + lengths, the MD5 of
+          every track's PCM (multi-buffer SIMD on the host cores) and the final stream
+          headers all inside the timed region.  The corpus is split over the ranks
+          (strong scaling); value = corpus samples / max-over-ranks wall time.
+  e2e_single_stream  ONE 1-hour stream through flake_b200_encode_stream (int32 in, the
+          flake_encode_frame convention): bounded by the stream's serial MD5 chain on one
+          host core, whatever the GPU does.
+  parity  the single-stream output byte-compared with the compiled reference over the
+          WHOLE stream, plus a sample of corpus tracks: frames compared / mismatching,
+          compressed size delta.
   other_configs  C1 / C3 / C4 of BASELINE.json: device-resident rate, stage times,
           roofline of their dominant kernel, parity against the reference.
-  e2e_corpus     a FIXED corpus of 1 h streams through flake_b200_encode_corpus (one
-          process drives every GPU it is given): strong scaling over --gpus.
 
 All arms and the full-size parity tests draw their PCM from ONE generator
 (flake_b200.synth.long_pcm, CPU, deterministic).
@@ -66,6 +72,9 @@ CONFIGS = {
 C2 = CONFIGS["C2"]
 RATE, CHANNELS, BPS, LEVEL, BLOCK = C2["rate"], C2["ch"], C2["bps"], C2["level"], C2["block"]
 C2_SAMPLES = C2["samples"]
+# the e2e corpus (same format and level as C2): E2E_TRACKS tracks of E2E_TRACK_SAMPLES samples
+E2E_TRACKS = 128
+E2E_TRACK_SAMPLES = 225 * RATE            # 3 min 45 s: 2423 blocks of 4096 (the last one short)
 
 
 def env_int(name, default):
@@ -223,37 +232,41 @@ def parity_record(got: np.ndarray, flen: np.ndarray, fbs: np.ndarray, want: np.n
     return rec
 
 
-def run_reference_arm(args):
-    """The reference's own CPU implementation on this box's host cores.
+def corpus_track_i32(index, nsamples):
+    from flake_b200 import synth
+    return synth.corpus_track(index, nsamples, CHANNELS, BPS, RATE)
 
-    The workload of the GPU arm is one 1-hour stream per rank.  libflake is single threaded
-    and its API is serial per stream (frame numbers and the MD5 chain through every block), so
-    the most host threads the reference can use on this workload is one per stream:
-    `--gpus N` streams -> N threads, one FlakeContext each.  Each step encodes a bounded sample
-    (the first ~4.4 min of audio) of the GPU arm's own stream (same generator, same seed).  For
-    orientation the line also carries `all_cores`: every host core busy, each on its own block
-    range -- more parallelism than the API offers one stream, i.e. what a corpus of many files
-    would reach.
+
+def run_reference_arm(args):
+    """The reference's own CPU implementation on this box's host cores -- all of them.
+
+    libflake is single threaded and its API is serial per stream (frame numbers and the MD5
+    chain through every block), so the way the reference uses a whole box is one file per
+    core: exactly the shape of the GPU arm's e2e workload (a corpus of independent tracks).
+    Each step encodes a bounded sample of that corpus: the first `cores` tracks, a prefix of
+    each (same generator, same track indices as the GPU arm), one thread and one reference
+    context per track, every block through flake_encode_frame in a C loop.  `single_thread`
+    is one track on one core, for orientation.
     """
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    streams = max(1, min(args.gpus, cores))
-    threads = env_int("FLAKE_BENCH_REF_THREADS", streams)
-    per_thread = env_int("FLAKE_BENCH_REF_SAMPLES_PER_THREAD", BLOCK * 2800)   # 11.5 M samples, ~1 s of CPU
-    pcm = workload_pcm(C2, 0, per_thread * threads)
+    threads = env_int("FLAKE_BENCH_REF_THREADS", cores)
+    per_thread = env_int("FLAKE_BENCH_REF_SAMPLES_PER_THREAD", BLOCK * 700)      # 2.9 M samples, ~0.25 s of CPU
+    per_thread = min(per_thread, E2E_TRACK_SAMPLES // BLOCK * BLOCK)
+    ntracks = env_int("FLAKE_BENCH_E2E_TRACKS", E2E_TRACKS)
+    pcm = np.concatenate([corpus_track_i32(t % ntracks, per_thread) for t in range(threads)])
     total, times, kind, _ = cpu_reference_time(pcm, C2, threads, args.steps, max(1, min(args.warmup, 1)))
     ms = 1e3 * float(np.mean(times))
     val = total / (ms * 1e-3) / 1e6
-    sample = "%d block range(s) x %d samples (%.0f s of audio) of the GPU arm's rank-0 stream per step, " \
-             "one thread + one reference context per range, C loop over flake_encode_frame" % (
-                 threads, total // threads, total / threads / RATE)
-    allc = None
-    if cores > threads and not os.environ.get("FLAKE_BENCH_SKIP_ALL_CORES"):
-        t2, times2, _, _ = cpu_reference_time(workload_pcm(C2, 0, BLOCK * 700 * cores), C2, cores, 1, 1)
-        allc = {"value": round(t2 / times2[0] / 1e6, 3), "unit": "MSamples/s", "cores": cores,
-                "sample": "%d block ranges of %d samples" % (cores, t2 // cores)}
+    sample = "the first %d samples (%.0f s of audio) of corpus tracks 0..%d per step, one thread + one reference " \
+             "context per track, C loop over flake_encode_frame" % (per_thread, per_thread / RATE, threads - 1)
+    one = None
+    if not os.environ.get("FLAKE_BENCH_SKIP_SINGLE_THREAD"):
+        t1, times1, _, _ = cpu_reference_time(pcm[:per_thread * 2], C2, 1, 1, 0)
+        one = {"value": round(t1 / times1[0] / 1e6, 3), "unit": "MSamples/s", "cores": 1,
+               "sample": "%d samples on one thread" % t1}
     line = {
         "impl": "reference", "metric": "MSamples/s encoded, flake -8", "value": round(val, 3),
         "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -264,16 +277,21 @@ def run_reference_arm(args):
                          "sample": sample, "host_cores_available": cores},
         "e2e": {"value": round(val, 3), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "audio_seconds_per_s": round(val * 1e6 / RATE, 1),
-        "all_cores": allc,
+        "single_thread": one,
     }
     print(json.dumps(line), flush=True)
 
 
 def workload_config(n_gpus):
+    ntracks = env_int("FLAKE_BENCH_E2E_TRACKS", E2E_TRACKS)
     return {"workload": "C2: " + C2["what"] + " = 158760000 samples, 38760 blocks of 4096, per GPU",
+            "e2e_workload": "C5 shape, same format and level: a fixed corpus of %d independent tracks x %d samples "
+                            "(%.1f h of audio in all), split over the ranks; both arms may use every host core" % (
+                                ntracks, E2E_TRACK_SAMPLES, ntracks * E2E_TRACK_SAMPLES / RATE / 3600.0),
             "level": LEVEL, "block_size": BLOCK, "channels": CHANNELS, "bits_per_sample": BPS,
             "sample_rate": RATE, "samples_per_gpu": C2_SAMPLES,
-            "generator": "flake_b200.synth.long_pcm(seed = rank), the same in both arms",
+            "generator": "flake_b200.synth.long_pcm(seed = rank) for the 1 h stream, synth.corpus_track(i) for "
+                         "the corpus; the same in both arms",
             "l2": "inputs (635 MB packed PCM per pass) larger than the 126 MB L2; no explicit flush",
             "sharding": "one stream per rank, no collective" if n_gpus > 1 else "single stream"}
 
@@ -480,7 +498,7 @@ def run_gpu_arm(args):
         rank_ms = [round(float(x.item()), 3) for x in g]
 
     # ---- end-to-end through the host-buffer C ABI -----------------------------------
-    e2e_steps = max(1, min(args.steps, env_int("FLAKE_BENCH_E2E_STEPS", 3)))
+    e2e_steps = max(1, min(args.steps, env_int("FLAKE_BENCH_SINGLE_STEPS", 2)))
     h_pcm32 = torch.from_numpy(pcm_np).pin_memory()
     pcm_pinned = h_pcm32.numpy()
     ctx0 = C.byref(dp.enc.ctx)
@@ -512,19 +530,15 @@ def run_gpu_arm(args):
             md5_hex = bytes(si.md5sum).hex()
     e2e_stats = enc2.stats()
     enc2.close()
-    clk = clocks.stop() if rank == 0 else None
     e2e_ms_max = allmax(float(np.mean(e2e_ms)))
     e2e_value = world * nsamples / (e2e_ms_max * 1e-3) / 1e6
+    single_out = h_out[:e2e_bytes].numpy().copy() if rank == 0 else None     # for the parity leg below
 
-    # ---- corpus shape (C5) through the C corpus entry point: strong scaling -------------
-    corpus = None
-    if rank == 0 and not os.environ.get("FLAKE_BENCH_SKIP_CORPUS") and hasattr(lib, "flake_b200_encode_corpus"):
-        try:
-            corpus = run_corpus_leg(lib, api, pcm_pinned, nsamples, world, torch)
-        except Exception as exc:            # informative only
-            corpus = {"value": None, "error": str(exc)[:300]}
-    if world > 1:
-        dist.barrier(group=host_group)      # the other ranks wait on the host: rank 0 used their GPUs
+    # ---- e2e: the fixed corpus through flake_b200_encode_corpus, split over the ranks ------
+    del h_out, h_pcm32, pcm_pinned
+    corpus_rec = run_corpus_leg(lib, api, torch, dist, rank, world, local, host_group, allmax, barrier,
+                                max(1, min(args.steps, env_int("FLAKE_BENCH_E2E_STEPS", 3))))
+    clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
         dp.close()
@@ -550,7 +564,7 @@ def run_gpu_arm(args):
     parity = None
     cpu = None
     try:
-        got = h_out[:e2e_bytes].numpy()
+        got = single_out
         want, per_block, kind = reference_bytes(pcm_np, C2)
         parity = parity_record(got, h_flen[:nf.value].astype(np.int64), h_fbs[:nf.value].astype(np.int64),
                                want, per_block, C2, kind)
@@ -573,7 +587,7 @@ def run_gpu_arm(args):
     # ---- the other BASELINE.json configurations -----------------------------------------
     others = {}
     dp.close()
-    del dp, h_pcm32, pcm_pinned
+    del dp
     if not os.environ.get("FLAKE_BENCH_SKIP_OTHERS"):
         for name in ("C1", "C3", "C4"):
             try:
@@ -589,16 +603,18 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
         "config": workload_config(world),
         "audio_seconds_per_s": round(value * 1e6 / RATE, 1),
-        "e2e": {"value": round(e2e_value, 2), "unit": "MSamples/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms_max, 2),
-                "input": "int32 interleaved host buffer (flake_encode_frame convention)",
-                "includes": "H2D, all kernels, D2H of frames+lengths, MD5 of the PCM, final STREAMINFO",
-                "md5": md5_hex,
-                "md5_thread_ms": round(e2e_stats.md5_ms / (1 + e2e_steps), 1),
-                "gpu_ms": round(e2e_stats.gpu_ms / (1 + e2e_steps), 1),
-                "wall": "one stream's MD5 is a serial chain on one host core; see md5_thread_ms"},
+        "e2e": corpus_rec,
+        "e2e_single_stream": {
+            "value": round(e2e_value, 2), "unit": "MSamples/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms_max, 2),
+            "workload": "one 1 h stream per rank through flake_b200_encode_stream",
+            "input": "int32 interleaved host buffer (flake_encode_frame convention)",
+            "includes": "H2D, all kernels, D2H of frames+lengths, MD5 of the PCM, final STREAMINFO",
+            "md5": md5_hex,
+            "md5_thread_ms": round(e2e_stats.md5_ms, 1),
+            "gpu_ms": round(e2e_stats.gpu_ms, 1),
+            "wall": "one stream's MD5 is a serial chain on one host core (md5_thread_ms of ms_per_step)"},
         "parity": parity,
-        "e2e_corpus": corpus,
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roofline,
@@ -652,13 +668,127 @@ def run_other_config(lib, name, dev, stream, peak_gbs, peak_src, traffic, torch)
     return rec
 
 
-def run_corpus_leg(lib, api, pcm_pinned, nsamples, world, torch):
-    """A FIXED corpus of 1 h C2 streams through flake_b200_encode_corpus, ONE process driving
-    `world` GPUs with library-owned threads (strong scaling over --gpus; the other ranks idle)."""
-    from flake_b200 import corpus as fc
-    nstreams = env_int("FLAKE_BENCH_CORPUS_STREAMS", 16)
-    ngpu = min(world, torch.cuda.device_count())
-    return fc.bench_corpus(lib, pcm_pinned, nsamples, CHANNELS, RATE, BPS, LEVEL, nstreams, list(range(ngpu)))
+def pcie_probe(torch, dev, nbytes=1 << 30):
+    """Pinned host <-> device copy rate of this GPU's link, GB/s (h2d, d2h): what bounds the e2e leg."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = []
+    for src, dst in ((h, d), (d, h)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out.append(round(3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9, 1))
+    return out
+
+
+def run_corpus_leg(lib, api, torch, dist, rank, world, local, host_group, allmax, barrier, steps):
+    """e2e: the fixed corpus (E2E_TRACKS tracks, packed s16le in page-locked host memory) through
+    flake_b200_encode_corpus.  Rank r takes tracks r, r + world, ...; one library call per step
+    encodes them on this rank's GPU (two worker threads, DMA straight from / to the caller's
+    buffers) while cores/world MD5 workers hash them in SIMD lanes.  Timed with the host clock
+    around the call (its inputs and outputs are host buffers), barrier before, max over ranks."""
+    from flake_b200 import corpus as fc, synth
+    ntracks = env_int("FLAKE_BENCH_E2E_TRACKS", E2E_TRACKS)
+    n = env_int("FLAKE_BENCH_E2E_TRACK_SAMPLES", E2E_TRACK_SAMPLES)
+    mine = list(range(rank, ntracks, world))
+    cores = os.cpu_count() or 1
+    md5_threads = env_int("FLAKE_BENCH_MD5_THREADS", max(1, cores // world))
+    dev = torch.device("cuda", local)
+    co = fc.Corpus(lib, CHANNELS, RATE, BPS, LEVEL, api.PCM_S16LE, devices=[local], longest=n,
+                   md5_threads=md5_threads, threads_per_device=env_int("FLAKE_BENCH_GPU_THREADS", 2))
+    cap = co.max_encoded_size(n)
+    fcap = co.frame_cap(n)
+    h_in = torch.empty((len(mine), n, CHANNELS), dtype=torch.int16).pin_memory()
+    h_out = torch.empty((len(mine), cap), dtype=torch.uint8).pin_memory()
+    flen = np.zeros((len(mine), fcap), dtype=np.uint32)
+    fbs = np.zeros((len(mine), fcap), dtype=np.uint32)
+    in_np, out_np = h_in.numpy(), h_out.numpy()
+    for j, t in enumerate(mine):
+        synth.corpus_track(t, n, CHANNELS, BPS, RATE, out=in_np[j])
+    items = (api.FlakeB200CorpusStream * max(1, len(mine)))()
+    for j in range(len(mine)):
+        it = items[j]
+        it.pcm = in_np[j].ctypes.data; it.nsamples = n
+        it.out = out_np[j].ctypes.data; it.out_cap = cap
+        it.frame_len = flen[j].ctypes.data; it.frame_bs = fbs[j].ctypes.data; it.frame_cap = fcap
+    stats = api.FlakeB200CorpusStats()
+    hdr = (C.c_ubyte * 16384)()
+    times = []
+    for itn in range(1 + steps):
+        barrier()
+        t0 = time.perf_counter()
+        rc = lib.flake_b200_corpus_encode(co.handle, items, len(mine), C.byref(stats))
+        for j in range(len(mine)):                       # the final stream headers: the streams are complete files
+            lib.flake_b200_corpus_stream_header(C.byref(co.ctx), C.byref(items[j]), hdr, len(hdr))
+        dt = time.perf_counter() - t0
+        if rc < 0:
+            raise RuntimeError("flake_b200_corpus_encode failed: %d %s" % (rc, stats.error.decode(errors="replace")))
+        if itn >= 1:
+            times.append(dt * 1e3)
+    my_ms = float(np.mean(times))
+    ms = allmax(my_ms)
+    total_samples = ntracks * n
+    rank_ms = None
+    if world > 1:
+        g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([my_ms], dtype=torch.float64, device=dev))
+        rank_ms = [round(float(x.item()), 2) for x in g]
+    h2d = torch.tensor([float(stats.h2d_bytes), float(stats.d2h_bytes), float(stats.kernel_launches)],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(h2d)
+    h2d_b, d2h_b, launches = (int(x) for x in h2d.tolist())
+    rec = None
+    if rank == 0:
+        # parity of a sample of this rank's tracks against the reference (untimed)
+        par = {"tracks_compared": 0, "frames_compared": 0, "frames_mismatching": 0, "md5_mismatching": 0}
+        try:
+            for j in range(min(len(mine), env_int("FLAKE_BENCH_E2E_PARITY_TRACKS", 4))):
+                pcm32 = in_np[j].astype(np.int32)
+                want, per_block, kind = reference_bytes(pcm32, C2)
+                r = parity_record(out_np[j][:items[j].bytes], flen[j][:items[j].nframes].astype(np.int64),
+                                  fbs[j][:items[j].nframes].astype(np.int64), want, per_block, C2, kind)
+                par["tracks_compared"] += 1
+                par["frames_compared"] += r["frames_compared"]
+                par["frames_mismatching"] += r["frames_mismatching"]
+                par["md5_mismatching"] += int(bytes(items[j].md5sum) != hashlib.md5(in_np[j].tobytes()).digest())
+                par["against"] = kind
+        except Exception as exc:
+            par["error"] = str(exc)[:200]
+        pcie = None
+        try:
+            pcie = pcie_probe(torch, dev)
+        except Exception:
+            pass
+        rec = {"value": round(total_samples / (ms * 1e-3) / 1e6, 2), "unit": "MSamples/s",
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "ms_per_step": round(ms, 2),
+               "scaling": "strong", "workload": "fixed corpus: %d tracks x %d samples (%.0f s each, %.2f h in all), "
+               "flake -8, 16-bit stereo 44.1 kHz, packed s16le in page-locked host memory; tracks r, r+N, ... on rank r"
+               % (ntracks, n, n / RATE, total_samples / RATE / 3600.0),
+               "includes": "H2D from the caller's buffers, all kernels, D2H of frames + lengths into the caller's buffers, "
+                           "MD5 of every track, final stream headers",
+               "api": "flake_b200_corpus_encode (one call per rank and step)",
+               "audio_seconds_per_s": round(total_samples / (ms * 1e-3) / RATE, 1),
+               "tracks": ntracks, "tracks_per_rank": len(mine), "rank_ms_per_step": rank_ms,
+               "gpu_launches_per_step": launches,
+               "rank0": {"md5_ms": round(stats.md5_ms, 2), "md5_threads": int(stats.md5_threads),
+                         "md5_lanes_per_thread": int(stats.md5_lanes), "gpu_threads": int(stats.gpu_threads),
+                         "chunks": int(stats.chunks), "gpu_worker_ms": round(stats.device_ms[0], 2),
+                         "h2d_gbs": round(stats.h2d_bytes / (my_ms * 1e-3) / 1e9, 1),
+                         "d2h_gbs": round(stats.d2h_bytes / (my_ms * 1e-3) / 1e9, 1),
+                         "host_cores": cores},
+               "pcie_probe_gbs": {"h2d": pcie[0], "d2h": pcie[1]} if pcie else None,
+               "parity": par}
+    co.close()
+    del h_in, h_out
+    if world > 1:
+        dist.barrier(group=host_group)
+    return rec
 
 
 def main():

@@ -57,6 +57,31 @@ class FlakeB200Stats(C.Structure):
                 ("wall_ms", C.c_double)]
 
 
+MAX_DEVICES = 16
+
+
+class FlakeB200CorpusStream(C.Structure):
+    """One stream of a flake_b200_encode_corpus call (include/flake_b200.h)."""
+    _fields_ = [("pcm", C.c_void_p), ("nsamples", C.c_ulonglong), ("out", C.c_void_p),
+                ("out_cap", C.c_ulonglong), ("frame_len", C.c_void_p), ("frame_bs", C.c_void_p),
+                ("frame_cap", C.c_uint), ("bytes", C.c_longlong), ("nframes", C.c_uint),
+                ("max_frame_size", C.c_uint), ("verbatim_frames", C.c_uint), ("md5sum", C.c_ubyte * 16)]
+
+
+class FlakeB200CorpusOptions(C.Structure):
+    _fields_ = [("threads_per_device", C.c_int), ("md5_threads", C.c_int), ("chunk_blocks", C.c_int)]
+
+
+class FlakeB200CorpusStats(C.Structure):
+    _fields_ = [("wall_ms", C.c_double), ("md5_ms", C.c_double), ("streams", C.c_ulonglong),
+                ("samples", C.c_ulonglong), ("bytes", C.c_ulonglong), ("chunks", C.c_ulonglong),
+                ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong), ("kernel_launches", C.c_ulonglong),
+                ("chunk_blocks", C.c_uint), ("devices", C.c_int), ("gpu_threads", C.c_int),
+                ("md5_threads", C.c_int), ("md5_lanes", C.c_int),
+                ("device_ms", C.c_double * MAX_DEVICES), ("device_samples", C.c_ulonglong * MAX_DEVICES),
+                ("error", C.c_char * 256)]
+
+
 class FbSub(C.Structure):
     """Per-subframe decision record (flake_b200/csrc/engine.h FbSub)."""
     _fields_ = [("type", C.c_int32), ("order", C.c_int32), ("obits", C.c_int32),
@@ -116,6 +141,17 @@ def load_library(path: Optional[str] = None, extension: bool = True) -> C.CDLL:
         lib.flake_b200_get_stats.argtypes = [P(FlakeContext), P(FlakeB200Stats)]; lib.flake_b200_get_stats.restype = C.c_int
         lib.flake_b200_last_error.argtypes = [P(FlakeContext)]; lib.flake_b200_last_error.restype = C.c_char_p
         lib.flake_b200_version.argtypes = []; lib.flake_b200_version.restype = C.c_char_p
+        lib.flake_b200_encode_corpus.argtypes = [P(FlakeContext), C.c_int, P(FlakeB200CorpusStream), C.c_uint,
+                                                 P(C.c_int), C.c_int, P(FlakeB200CorpusOptions), P(FlakeB200CorpusStats)]
+        lib.flake_b200_encode_corpus.restype = C.c_int
+        lib.flake_b200_corpus_open.argtypes = [P(FlakeContext), C.c_int, P(C.c_int), C.c_int, P(FlakeB200CorpusOptions)]
+        lib.flake_b200_corpus_open.restype = C.c_void_p
+        lib.flake_b200_corpus_encode.argtypes = [C.c_void_p, P(FlakeB200CorpusStream), C.c_uint, P(FlakeB200CorpusStats)]
+        lib.flake_b200_corpus_encode.restype = C.c_int
+        lib.flake_b200_corpus_close.argtypes = [C.c_void_p]; lib.flake_b200_corpus_close.restype = None
+        lib.flake_b200_corpus_error.argtypes = [C.c_void_p]; lib.flake_b200_corpus_error.restype = C.c_char_p
+        lib.flake_b200_corpus_stream_header.argtypes = [P(FlakeContext), P(FlakeB200CorpusStream), C.c_void_p, C.c_uint]
+        lib.flake_b200_corpus_stream_header.restype = C.c_int
         if lib.flake_b200_subframe_record_size() != C.sizeof(FbSub):
             raise FlakeLibraryError("FbSub layout mismatch between api.py and the library")
     return lib
@@ -195,9 +231,16 @@ class Encoder:
     def encode_stream(self, pcm: np.ndarray, pcm_format: int = PCM_S32,
                       nsamples: Optional[int] = None, want_sizes: bool = True):
         """Batch encode from host memory.  Returns (bytes, frame_len, frame_bs)."""
-        arr = np.ascontiguousarray(pcm)
+        if pcm_format == PCM_S32:
+            arr = np.ascontiguousarray(pcm, dtype=np.int32)      # the C side reads nsamples * channels int32
+        else:
+            arr = np.ascontiguousarray(pcm)
         if nsamples is None:
             nsamples = arr.shape[0]
+        need = int(nsamples) * int(self.ctx.channels) * {PCM_S32: 4, PCM_S16LE: 2, PCM_S24LE: 3, PCM_S8: 1}[pcm_format]
+        if arr.nbytes < need:
+            raise ValueError("pcm holds %d bytes, %d samples x %d channels need %d" % (
+                arr.nbytes, nsamples, self.ctx.channels, need))
         cap = int(self.lib.flake_b200_max_encoded_size(C.byref(self.ctx), nsamples))
         out = np.empty(cap, dtype=np.uint8)
         bs = int(self.ctx.params.block_size)

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 ]
 
 
-HOST_C = ("flake_host.c", "md5.c", "md5_mb.c")      # the C host layer (gcc)
+HOST_C = ("flake_host.c", "flake_corpus.c", "md5.c", "md5_mb.c")      # the C host layer (gcc)
 
 
 def _run(cmd, cwd=None):

@@ -751,12 +751,13 @@ static int ensure_batch_engine(FbCtx *c)
 
 unsigned long long flake_b200_max_encoded_size(const FlakeContext *s, unsigned long long nsamples)
 {
-    if (!s || !s->private_ctx) return 0;
-    const FbCtx *c = (const FbCtx *)s->private_ctx;
-    const unsigned long long B = (unsigned long long)c->params.block_size;
+    /* from the public fields: also valid for a context that was never initialised (the prototype
+     * of flake_b200_encode_corpus) */
+    if (!s || s->params.block_size < 1) return 0;
+    const unsigned long long B = (unsigned long long)s->params.block_size;
     unsigned long long frames = (nsamples + B - 1) / B;
-    if (c->params.variable_block_size) frames *= 8;
-    return frames * 96ull + ((nsamples * (unsigned long long)(c->channels * c->bps + 1) + 7) >> 3) + 64;
+    if (s->params.variable_block_size) frames *= 8;
+    return frames * 96ull + ((nsamples * (unsigned long long)(s->channels * s->bits_per_sample + 1) + 7) >> 3) + 64;
 }
 
 long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,

@@ -122,6 +122,35 @@ def long_pcm(nsamples: int, channels: int, bps: int, sample_rate: int, seed: int
     return out
 
 
+_TRACK_BASES: dict = {}
+
+
+def corpus_track(index: int, nsamples: int, channels: int, bps: int, sample_rate: int,
+                 out: np.ndarray = None, nbases: int = 8, base_seconds: float = 40.0) -> np.ndarray:
+    """Track `index` of a synthetic corpus (many files of one format): like long_pcm, tiles of a
+    `base_seconds` "mix" segment with a different gain per tile, but the segment is one of
+    `nbases` cached ones, entered at a track-specific offset, so that a corpus of hundreds of
+    tracks costs seconds to generate and no two tracks hold the same samples.  Writes into `out`
+    (any integer dtype that holds `bps` bits, shape (nsamples, channels)) when given."""
+    key = (index % nbases, channels, bps, sample_rate, base_seconds)
+    if key not in _TRACK_BASES:
+        n0 = int(round(sample_rate * base_seconds))
+        _TRACK_BASES[key] = synth_pcm(n0, channels, bps, sample_rate, seed=1000 + key[0]).astype(np.float32)
+    base = _TRACK_BASES[key]
+    n0 = base.shape[0]
+    rng = np.random.Generator(np.random.PCG64(SEED_BASE + 104729 * (index + 1)))
+    if out is None:
+        out = np.empty((nsamples, channels), dtype=np.int32)
+    pos, off = 0, int(rng.integers(0, n0))
+    while pos < nsamples:
+        g = np.float32(rng.uniform(0.3, 1.0))
+        take = min(nsamples - pos, n0 - off)
+        out[pos:pos + take] = np.rint(base[off:off + take] * g)
+        pos += take
+        off = 0
+    return out
+
+
 def pack_pcm(pcm: np.ndarray, bps: int) -> bytes:
     """Little-endian packed sample bytes at ceil(bps/8) bytes per sample (WAV data chunk)."""
     nbytes = (bps + 7) // 8

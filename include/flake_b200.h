@@ -145,6 +145,88 @@ FLAKE_API long long flake_b200_write_seektable(const unsigned int *frame_len, co
                                                unsigned int nframes, unsigned int interval_samples,
                                                unsigned char *data, unsigned long long cap);
 
+/*
+ * Many streams over the GPUs of one box, from one process -- the batch form of running the
+ * flake/flake.c:612-678 loop once per file of a corpus, and of SURVEY.md 8(e): a stream is cut
+ * into chunks of consecutive blocks, any GPU of `devices` encodes any chunk (no exchange
+ * between GPUs), and the host prefix-sums the chunk sizes into frame offsets.  One stream with
+ * several devices is "one stream split by frame range over the GPUs".
+ *
+ * All streams share the format and parameters of `proto` (channels, sample_rate,
+ * bits_per_sample, params: a FlakeContext as the caller would hand to flake_encode_init; it
+ * need not be initialised and is not modified).  `pcm_format`: FLAKE_B200_PCM_S32, or the
+ * packed layout whose container is ceil(bits_per_sample / 8) bytes (what a WAV data chunk
+ * holds).  Buffers are HOST memory; page-locked buffers (cudaHostAlloc / cudaHostRegister)
+ * are read and written by DMA directly, pageable ones go through a staging copy.
+ *
+ * Per stream the call produces exactly what flake_encode_init + the flake_encode_frame loop
+ * would have: the frame bytes, their lengths and block sizes, STREAMINFO's maximum frame size
+ * (seeded with the verbatim bound, encode.c:446-450, 967) and the MD5 of the PCM
+ * (encode.c:1006), hashed by library threads that advance up to 32 streams per core at once.
+ * flake_b200_corpus_stream_header() then writes the stream header with the final STREAMINFO.
+ *
+ * Returns 0, or the first negative stream result: -1 bad arguments, -2 a stream's `out` or
+ * frame arrays too small, -3 CUDA failure / no device (FlakeB200CorpusStats.error says which).
+ */
+#define FLAKE_B200_MAX_DEVICES 16
+
+typedef struct FlakeB200CorpusStream {
+    /* in */
+    const void *pcm;                    /* channel-interleaved samples, `pcm_format`            */
+    unsigned long long nsamples;        /* inter-channel samples (< 2^32, STREAMINFO's field)   */
+    unsigned char *out;                 /* frames, back to back                                  */
+    unsigned long long out_cap;         /* >= flake_b200_max_encoded_size() is always enough     */
+    unsigned int *frame_len, *frame_bs; /* optional, frame_cap entries each                      */
+    unsigned int frame_cap;
+    /* out */
+    long long bytes;                    /* frame bytes written, or a negative error              */
+    unsigned int nframes;
+    unsigned int max_frame_size;
+    unsigned int verbatim_frames;
+    unsigned char md5sum[16];
+} FlakeB200CorpusStream;
+
+typedef struct FlakeB200CorpusOptions {
+    int threads_per_device;             /* GPU worker threads per device, 0 = default (2)        */
+    int md5_threads;                    /* 0 = one per online CPU (never more than streams)      */
+    int chunk_blocks;                   /* blocks per engine pass, 0 = default                   */
+} FlakeB200CorpusOptions;
+
+typedef struct FlakeB200CorpusStats {
+    double wall_ms;
+    double md5_ms;                      /* the MD5 worker that finished last                     */
+    unsigned long long streams, samples, bytes, chunks;
+    unsigned long long h2d_bytes, d2h_bytes, kernel_launches;
+    unsigned int chunk_blocks;
+    int devices, gpu_threads, md5_threads, md5_lanes;
+    double device_ms[FLAKE_B200_MAX_DEVICES];                 /* per entry of `devices`: worker wall time */
+    unsigned long long device_samples[FLAKE_B200_MAX_DEVICES]; /* samples encoded by that device   */
+    char error[256];
+} FlakeB200CorpusStats;
+
+FLAKE_API int flake_b200_encode_corpus(const FlakeContext *proto, int pcm_format,
+                                       FlakeB200CorpusStream *streams, unsigned int nstreams,
+                                       const int *devices, int ndevices,      /* NULL / 0: every device */
+                                       const FlakeB200CorpusOptions *options, /* NULL: defaults */
+                                       FlakeB200CorpusStats *stats);          /* optional */
+/* The same with a handle that keeps the per-device engines, lanes and streams between calls
+ * (a corpus handed over in several batches pays the set-up once).  proto->samples, when not 0,
+ * announces the longest stream and bounds the chunk size. */
+typedef struct FlakeB200Corpus FlakeB200Corpus;
+FLAKE_API FlakeB200Corpus *flake_b200_corpus_open(const FlakeContext *proto, int pcm_format,
+                                                  const int *devices, int ndevices,
+                                                  const FlakeB200CorpusOptions *options);
+FLAKE_API int flake_b200_corpus_encode(FlakeB200Corpus *corpus, FlakeB200CorpusStream *streams,
+                                       unsigned int nstreams, FlakeB200CorpusStats *stats);
+FLAKE_API void flake_b200_corpus_close(FlakeB200Corpus *corpus);
+FLAKE_API const char *flake_b200_corpus_error(const FlakeB200Corpus *corpus);
+/* Stream header ("fLaC", final STREAMINFO, vendor comment, padding: what flake_encode_init
+ * leaves in FlakeContext.header, encode.c:125-156, after the CLI's final STREAMINFO rewrite,
+ * flake/flake.c:665-673) of one encoded stream of the corpus.  Returns the header length, the
+ * length needed when data == NULL, or -1. */
+FLAKE_API int flake_b200_corpus_stream_header(const FlakeContext *proto, const FlakeB200CorpusStream *stream,
+                                              unsigned char *data, unsigned int cap);
+
 FLAKE_API int flake_b200_get_stats(const FlakeContext *s, FlakeB200Stats *stats);
 FLAKE_API const char *flake_b200_last_error(const FlakeContext *s);
 FLAKE_API const char *flake_b200_version(void);

@@ -310,7 +310,11 @@ typedef void *cudaStream_t;
 typedef struct cuemu_event { double t; } *cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaEventDefault = 0, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum { cudaStreamNonBlocking = 1, cudaEventDefault = 0, cudaEventBlockingSync = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+/* page-locked or pageable: no difference here; CUEMU_ALL_PINNED=1 makes every host pointer report
+ * as page-locked so that the tests can drive both the direct and the staged host paths */
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
@@ -324,6 +328,12 @@ inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMallocHost(p, n); }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *)
+{
+    const char *e = getenv("CUEMU_ALL_PINNED");
+    a->type = (e && *e == '1') ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered;
+    return 0;
+}
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return 0; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return 0; }

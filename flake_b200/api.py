@@ -65,7 +65,8 @@ class FlakeB200CorpusStream(C.Structure):
     _fields_ = [("pcm", C.c_void_p), ("nsamples", C.c_ulonglong), ("out", C.c_void_p),
                 ("out_cap", C.c_ulonglong), ("frame_len", C.c_void_p), ("frame_bs", C.c_void_p),
                 ("frame_cap", C.c_uint), ("bytes", C.c_longlong), ("nframes", C.c_uint),
-                ("max_frame_size", C.c_uint), ("verbatim_frames", C.c_uint), ("md5sum", C.c_ubyte * 16)]
+                ("max_frame_size", C.c_uint), ("min_frame_size", C.c_uint), ("verbatim_frames", C.c_uint),
+                ("md5sum", C.c_ubyte * 16)]
 
 
 class FlakeB200CorpusOptions(C.Structure):
@@ -138,6 +139,7 @@ def load_library(path: Optional[str] = None, extension: bool = True) -> C.CDLL:
         lib.flake_b200_stage_times.restype = C.c_int
         lib.flake_b200_write_seektable.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_ulonglong]
         lib.flake_b200_write_seektable.restype = C.c_longlong
+        lib.flake_b200_set_streaminfo_sizes.argtypes = [P(FlakeContext), C.c_int]; lib.flake_b200_set_streaminfo_sizes.restype = C.c_int
         lib.flake_b200_get_stats.argtypes = [P(FlakeContext), P(FlakeB200Stats)]; lib.flake_b200_get_stats.restype = C.c_int
         lib.flake_b200_last_error.argtypes = [P(FlakeContext)]; lib.flake_b200_last_error.restype = C.c_char_p
         lib.flake_b200_version.argtypes = []; lib.flake_b200_version.restype = C.c_char_p

@@ -102,7 +102,7 @@ def build_oracle() -> str:
     if os.path.isdir("/root/reference/libflake"):
         _run(["make", "-C", ORACLE, "ref"])
         if os.path.exists(os.path.join(LIBDIR, "libflake.so")):
-            _run(["make", "-C", ORACLE, "_ref/flake_cli_b200"])
+            _run(["make", "-C", ORACLE, "_ref/flake_cli_b200", "_ref/flake_cli_b200_batch", "_ref/api_example_b200"])
     return os.path.join(ORACLE, "libflake_oracle.so")
 
 

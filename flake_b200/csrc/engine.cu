@@ -55,6 +55,10 @@ struct FbEngine {
     cudaEvent_t tev[FB_TIMING_RING][FB_NUM_STAGES + 1];
     double stage_ms[FB_NUM_STAGES];
     uint64_t stage_launches[FB_NUM_STAGES];
+    cudaEvent_t ev_pass;            /* end of the most recent pass: the scratch buffers are shared between passes */
+    cudaStream_t last_stream;       /* stream that pass ran on */
+    int have_pass;
+    int sync_launches;              /* FLAKE_B200_SYNC_LAUNCHES: name the kernel an asynchronous fault comes from */
     char err[256];
 };
 
@@ -158,6 +162,8 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     e->slot_bytes = (uint64_t)fb_slot_offset(e->max_frames, (uint32_t)e->max_samples, C, cfg->bps) + 256u;
     e->out_bytes = e->slot_bytes;
 
+    if (cudaEventCreateWithFlags(&e->ev_pass, cudaEventDisableTiming) != cudaSuccess) e->ev_pass = nullptr;
+    { const char *sl = getenv("FLAKE_B200_SYNC_LAUNCHES"); e->sync_launches = sl && *sl == '1'; }
     ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { set_err(err, errlen, "cudaStreamCreate failed", ce); delete e; return nullptr; }
 
@@ -252,6 +258,7 @@ extern "C" void fb_engine_destroy(FbEngine *e)
     cudaFree(e->d_frames); cudaFree(e->d_nframes); cudaFree(e->d_subs); cudaFree(e->d_modes);
     cudaFree(e->d_smp); cudaFree(e->d_res); cudaFree(e->d_coefs); cudaFree(e->d_shifts);
     cudaFree(e->d_slots); cudaFree(e->d_frame_len); cudaFree(e->d_frame_off);
+    if (e->ev_pass) cudaEventDestroy(e->ev_pass);
     cudaFree(e->d_vbs_sizes); cudaFree(e->d_vbs_counts); cudaFree(e->d_xpow32); cudaFree(e->d_crc16tab); cudaFree(e->d_status); cudaFree(e->d_plan);
     if (e->tev[0][0])
         for (int p = 0; p < FB_TIMING_RING; p++)
@@ -265,6 +272,19 @@ extern "C" uint32_t fb_engine_max_frames(const FbEngine *e) { return e ? e->max_
 extern "C" uint64_t fb_engine_out_capacity(const FbEngine *e) { return e ? e->out_bytes : 0; }
 extern "C" uint64_t fb_engine_launch_count(const FbEngine *e) { return e ? e->launches : 0; }
 extern "C" const char *fb_engine_last_error(const FbEngine *e) { return e ? e->err : "no engine"; }
+
+/* After every launch / memset of a pass: a failure is reported with the name of the step that
+ * caused it.  Launch-configuration errors show up here at once; a fault INSIDE a kernel is
+ * asynchronous and surfaces at a later call -- FLAKE_B200_SYNC_LAUNCHES=1 synchronises after
+ * every step so that the failing kernel is named (diagnosis only: it serialises the pass). */
+static int fb_step_failed(FbEngine *e, cudaStream_t st, cudaError_t ce, const char *what)
+{
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce == cudaSuccess && e->sync_launches) ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess) return 0;
+    snprintf(e->err, sizeof e->err, "%s failed: %s", what, cudaGetErrorString(ce));
+    return 1;
+}
 
 extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, uint64_t nsamples,
                                        uint32_t first_number, void *d_out, uint32_t *d_frame_len,
@@ -292,19 +312,31 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
         tev = e->tev[e->timing_passes++];
     }
 #define FB_MARK(i) do { if (tev) cudaEventRecord(tev[(i)], st); } while (0)
-    cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st);          /* frame count, -, pack ticket, - */
-    cudaMemsetAsync(e->d_status, 0, sizeof(unsigned long long) * (size_t)grid_frames, st);
-    cudaMemsetAsync(d_summary, 0, sizeof(FbSummary), st);
+    /* One engine = one set of scratch buffers (frame table, subframe records, residuals, look-back
+     * status): passes are serial.  A pass issued on another stream than the previous one waits for
+     * it, so callers may alternate streams without corrupting frames. */
+    if (e->have_pass && e->ev_pass && st != e->last_stream && cudaStreamWaitEvent(st, e->ev_pass, 0) != cudaSuccess) {
+        snprintf(e->err, sizeof e->err, "cudaStreamWaitEvent on the previous pass failed");
+        return -4;
+    }
+#define FB_STEP(call_, what_) do { if (fb_step_failed(e, st, (call_), (what_))) return -4; } while (0)
+#define FB_LAUNCHED(what_) FB_STEP(cudaSuccess, what_)
+    FB_STEP(cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st), "clearing the frame count");   /* frame count, -, pack ticket, - */
+    FB_STEP(cudaMemsetAsync(e->d_status, 0, sizeof(unsigned long long) * (size_t)grid_frames, st), "clearing the look-back status");
+    FB_STEP(cudaMemsetAsync(d_summary, 0, sizeof(FbSummary), st), "clearing the chunk summary");
     FB_MARK(0);
     if (cfg.variable_block_size) {
         FB_LAUNCH(k_vbs_split, dim3(nblocks), dim3(FB_PREP_THREADS), 0, st,
                   cfg, d_pcm, fmt, ns, e->d_vbs_sizes, e->d_vbs_counts);
+        FB_LAUNCHED("k_vbs_split");
         FB_LAUNCH(k_frames_vbs, dim3(1), dim3(1024), 0, st,
                   cfg, ns, first_number, e->d_vbs_sizes, e->d_vbs_counts, e->d_frames, e->d_nframes);
+        FB_LAUNCHED("k_frames_vbs");
         e->launches += 2;
     } else {
         FB_LAUNCH(k_frames_fixed, dim3((nblocks + 255) / 256), dim3(256), 0, st,
                   cfg, ns, first_number, e->d_frames, e->d_nframes);
+        FB_LAUNCHED("k_frames_fixed");
         e->launches += 1;
     }
     FB_MARK(1);
@@ -312,6 +344,7 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
                                          (unsigned long long)(fmt == FB_PCM_S16LE ? 2 : fmt == FB_PCM_S24LE ? 3 : fmt == FB_PCM_S8 ? 1 : 4);
     FB_LAUNCH(k_prep, dim3(grid_frames), dim3(FB_PREP_THREADS), 0, st,
               cfg, d_pcm, fmt, pcm_bytes, e->d_frames, e->d_nframes, e->d_smp, e->d_subs, e->d_modes);
+    FB_LAUNCHED("k_prep");
     e->launches += 1;
     FB_MARK(2);
     if (cfg.prediction_type == 2) {
@@ -346,6 +379,7 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
 #undef FB_LPC_GO3
 #undef FB_LPC_GO2
 #undef FB_LPC_GO
+        FB_LAUNCHED("k_lpc");
         e->launches += 1;
     }
     FB_MARK(3);
@@ -358,6 +392,7 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
                   cfg, e->d_frames, e->d_nframes, d_pcm, fmt, pcm_bytes, e->d_modes, e->d_smp, e->d_res, e->d_subs,
                   e->d_coefs, e->d_shifts, e->d_plan, e->search_smem_ints);
     }
+    FB_LAUNCHED(cfg.prediction_type == 2 && cfg.max_order > 12 ? "k_search<32>" : "k_search<12>");
     FB_MARK(4);
     /* threads per frame by the work in it (measured: 8192 samples per frame 1.75 ms with 128 threads vs
      * 1.88 with 256 per C2 stream; 32768 samples per frame 2.79 vs 2.08) */
@@ -366,14 +401,13 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
               cfg, e->d_frames, e->d_nframes, d_pcm, fmt, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
               flen, d_frame_bs, e->pack_smem_words, e->d_xpow32, e->d_crc16tab,
               e->d_nframes + 2, e->d_status, e->d_frame_off, (uint8_t *)d_out, d_summary);
+    FB_LAUNCHED("k_pack");
     FB_MARK(5);
 #undef FB_MARK
+#undef FB_LAUNCHED
+#undef FB_STEP
     e->launches += 2;
-    cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) {
-        snprintf(e->err, sizeof e->err, "kernel launch failed: %s", cudaGetErrorString(ce));
-        return -4;
-    }
+    if (e->ev_pass && cudaEventRecord(e->ev_pass, st) == cudaSuccess) { e->last_stream = st; e->have_pass = 1; }
     return 0;
 }
 

@@ -65,7 +65,7 @@ typedef struct FbSummary {
     uint32_t max_frame_bytes;
     uint64_t total_bytes;
     uint32_t verbatim_frames;   /* frames that took the size fallback */
-    uint32_t reserved;
+    uint32_t min_frame_inv;     /* ~(bytes of the smallest frame); 0 = no frame (the summary starts zeroed) */
 } FbSummary;
 
 /*

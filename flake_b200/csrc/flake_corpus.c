@@ -48,7 +48,7 @@ typedef struct CoStream {
     uint32_t posted;            /* chunks [0, posted) are in the prefix sums below */
     uint64_t byte_prefix;
     uint32_t frame_prefix;
-    uint32_t max_frame, verbatim;
+    uint32_t max_frame, min_frame, verbatim;
     int in_pinned, out_pinned;
     int err;
 } CoStream;
@@ -262,6 +262,7 @@ static void lane_collect(CoWorker *w, CoLane *l)
         T->byte_prefix += sm.total_bytes;
         T->frame_prefix += sm.nframes;
         if (sm.max_frame_bytes > T->max_frame) T->max_frame = sm.max_frame_bytes;
+        if (sm.nframes && ~sm.min_frame_inv < T->min_frame) T->min_frame = ~sm.min_frame_inv;
         T->verbatim += sm.verbatim_frames;
     }
     T->posted++;
@@ -463,10 +464,12 @@ FlakeB200Corpus *flake_b200_corpus_open(const FlakeContext *proto, int pcm_forma
     if (co->per_dev > 8) co->per_dev = 8;
     long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
     if (ncpu < 1) ncpu = 1;
-    co->md5_threads = opt && opt->md5_threads > 0 ? opt->md5_threads : env_int("FLAKE_B200_CORPUS_MD5_THREADS", (int)ncpu);
-    if (co->md5_threads > CO_MAX_WORKERS) co->md5_threads = CO_MAX_WORKERS;
     co->ngw = co->ndev * co->per_dev;
     if (co->ngw > CO_MAX_WORKERS) co->ngw = CO_MAX_WORKERS;
+    /* cores the MD5 workers may take: all but one per GPU worker */
+    const int spare = (int)ncpu - co->ngw > 1 ? (int)ncpu - co->ngw : 1;
+    co->md5_threads = opt && opt->md5_threads > 0 ? opt->md5_threads : env_int("FLAKE_B200_CORPUS_MD5_THREADS", spare);
+    if (co->md5_threads > CO_MAX_WORKERS) co->md5_threads = CO_MAX_WORKERS;
     co->gw = (CoWorker *)calloc((size_t)co->ngw, sizeof(CoWorker));
     if (!co->gw) { free(co); return NULL; }
     /* workers of one device are neighbours in corpus order: worker i -> device i % ndev */
@@ -511,7 +514,7 @@ int flake_b200_corpus_encode(FlakeB200Corpus *co, FlakeB200CorpusStream *streams
     if (!co || (!streams && nstreams)) return -1;
     for (unsigned i = 0; i < nstreams; i++) {
         FlakeB200CorpusStream *S = &streams[i];
-        S->bytes = -1; S->nframes = 0; S->max_frame_size = 0; S->verbatim_frames = 0;
+        S->bytes = -1; S->nframes = 0; S->max_frame_size = 0; S->min_frame_size = 0; S->verbatim_frames = 0;
         memset(S->md5sum, 0, sizeof S->md5sum);
         if ((!S->pcm && S->nsamples) || (!S->out && S->nsamples) || S->nsamples > 0xffffffffull) return -1;
     }
@@ -529,6 +532,7 @@ int flake_b200_corpus_encode(FlakeB200Corpus *co, FlakeB200CorpusStream *streams
         co->st[i].first_unit = co->nunits;
         co->nunits += co->st[i].nchunks;
         co->st[i].max_frame = (uint32_t)fb_verbatim_bound(&co->cfg);
+        co->st[i].min_frame = 0xffffffffu;
         co->st[i].in_pinned = streams[i].pcm ? fb_cuda_host_is_pinned(streams[i].pcm) : 1;
         co->st[i].out_pinned = streams[i].out ? fb_cuda_host_is_pinned(streams[i].out) : 1;
     }
@@ -540,11 +544,25 @@ int flake_b200_corpus_encode(FlakeB200Corpus *co, FlakeB200CorpusStream *streams
     /* threads of this call */
     int nworkers = co->ngw;
     if ((uint32_t)nworkers > co->nunits) nworkers = (int)co->nunits;
-    int nmd5 = co->md5_threads;
-    if ((uint32_t)nmd5 > nstreams) nmd5 = (int)nstreams;
-    int lanes = nmd5 ? (int)((nstreams + (unsigned)nmd5 - 1) / (unsigned)nmd5) : 1;
-    if (lanes > fb_md5_mb_lanes()) lanes = fb_md5_mb_lanes();
-    if (lanes > FB_MD5_MB_MAX) lanes = FB_MD5_MB_MAX;
+    /* MD5 workers.  A stream hashed alone runs at the scalar rate (~0.8 GB/s); a stream in a SIMD
+     * lane at ~0.6 of that, whatever the number of busy lanes up to 16.  So: with no more streams
+     * than cores to spare, one scalar thread per stream; otherwise as few threads as keep 16 lanes
+     * each (the cores left over drive the GPUs and take the DMA interrupts), and only a corpus of
+     * more than 16 streams per core goes to 32 lanes. */
+    int avail = co->md5_threads;
+    if (avail < 1) avail = 1;
+    int nmd5, lanes;
+    const int simd = fb_md5_mb_lanes();
+    if (nstreams <= (unsigned)avail || simd <= 1) {
+        nmd5 = nstreams < (unsigned)avail ? (int)nstreams : avail;
+        lanes = 1;
+    } else {
+        nmd5 = (int)((nstreams + 15u) / 16u);
+        if (nmd5 > avail) nmd5 = avail;
+        lanes = (int)((nstreams + (unsigned)nmd5 - 1) / (unsigned)nmd5);
+        if (lanes > simd) lanes = simd;
+        if (lanes > FB_MD5_MB_MAX) lanes = FB_MD5_MB_MAX;
+    }
     MdWorker *mw = (MdWorker *)calloc((size_t)(nmd5 ? nmd5 : 1), sizeof(MdWorker));
     if (!mw) rc = -3;
     if (!rc) {
@@ -579,6 +597,7 @@ int flake_b200_corpus_encode(FlakeB200Corpus *co, FlakeB200CorpusStream *streams
             S->bytes = (long long)T->byte_prefix;
             S->nframes = T->frame_prefix;
             S->max_frame_size = T->max_frame;
+            S->min_frame_size = T->min_frame == 0xffffffffu ? 0 : T->min_frame;
             S->verbatim_frames = T->verbatim;
         }
     }

@@ -45,6 +45,8 @@ typedef struct FbCtx {
     int channels, samplerate, bps;
     uint32_t sample_count, frame_count;
     int max_frame_size;
+    uint32_t min_frame_size;        /* smallest frame so far, 0xffffffff = none yet */
+    int report_min_frame;           /* flake_b200_set_streaminfo_sizes */
     int last_frame;
     FbMd5 md5;
     FbConfig cfg;
@@ -66,7 +68,8 @@ typedef struct FbCtx {
     char err[256];
 } FbCtx;
 
-static int g_device = -2;           /* -2: not chosen yet */
+static int g_device = -2;           /* process default; -2: not chosen yet.  Accessed with __atomic builtins */
+static __thread int t_device = -1;  /* this thread's choice (flake_b200_set_thread_device), -1: none */
 struct FbCtx;
 static int default_chunk_blocks(const struct FbCtx *c, unsigned int stream_samples, uint64_t target_ints);
 
@@ -254,7 +257,8 @@ int flake_get_streaminfo(const FlakeContext *s, FlakeStreaminfo *si)
     si->min_block_size = (c->params.variable_block_size || c->params.allow_vbs)
                              ? 16u : (unsigned)c->params.block_size;
     si->max_block_size = (unsigned)c->params.block_size;
-    si->min_frame_size = 0;
+    /* the reference always leaves 0 = unknown (metadata.c:52); the real value is opt-in */
+    si->min_frame_size = (c->report_min_frame && c->min_frame_size != 0xffffffffu) ? c->min_frame_size : 0;
     si->max_frame_size = (unsigned)c->max_frame_size;
     si->sample_rate = (unsigned)c->samplerate;
     si->channels = (unsigned)c->channels;
@@ -463,16 +467,33 @@ static void ctx_free(FbCtx *c)
 }
 
 /* The CUDA current device is per host thread: every entry point that touches the device binds
- * the calling thread to the context's device first (callers may use one thread per stream). */
-static void ctx_bind_device(const FbCtx *c)
+ * the calling thread to the context's device first (callers may use one thread per stream) and
+ * puts the caller's device back before it returns. */
+static int ctx_bind_device(const FbCtx *c)
 {
-    if (c->device >= 0) fb_cuda_set_device(c->device);
+    if (c->device < 0) return -1;
+    const int prev = fb_cuda_current_device();
+    if (prev == c->device) return -1;
+    fb_cuda_set_device(c->device);
+    return prev;                    /* the caller's device, to be restored on the way out */
+}
+
+static void ctx_unbind_device(int prev)
+{
+    if (prev >= 0) fb_cuda_set_device(prev);
 }
 
 int flake_b200_set_device(int device)
 {
     if (device < 0 || device >= fb_cuda_device_count()) return -1;
-    g_device = device;
+    __atomic_store_n(&g_device, device, __ATOMIC_RELEASE);
+    return 0;
+}
+
+int flake_b200_set_thread_device(int device)
+{
+    if (device < -1 || device >= fb_cuda_device_count()) return -1;
+    t_device = device;
     return 0;
 }
 
@@ -513,7 +534,7 @@ int fb_verbatim_bound(const FbConfig *g)
     return 16 + ((g->block_size * g->channels * g->bps + 7) >> 3);
 }
 
-int flake_encode_init(FlakeContext *s)
+static int flake_encode_init_impl(FlakeContext *s)
 {
     if (!s) return -1;
     s->header = NULL;
@@ -545,11 +566,14 @@ int flake_encode_init(FlakeContext *s)
     fb_md5_init(&c->md5);
 
     /* GPU side: device, streams, the one-block engine */
-    if (g_device == -2) {
+    int gd = __atomic_load_n(&g_device, __ATOMIC_ACQUIRE);
+    if (gd == -2) {
         const char *env = getenv("FLAKE_B200_DEVICE");
-        g_device = env ? atoi(env) : -1;
+        int expect = -2;
+        gd = env ? atoi(env) : -1;
+        if (!__atomic_compare_exchange_n(&g_device, &expect, gd, 0, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) gd = expect;
     }
-    c->device = g_device >= 0 ? g_device : fb_cuda_current_device();
+    c->device = t_device >= 0 ? t_device : (gd >= 0 ? gd : fb_cuda_current_device());
     c->chunk_blocks = default_chunk_blocks(c, s->samples, FB_CHUNK_HOST_INTS);
     c->dev_chunk_blocks = default_chunk_blocks(c, s->samples, s->samples ? FB_CHUNK_DEVICE_INTS : FB_CHUNK_HOST_INTS);
     c->eng1 = fb_engine_create(g, c->device, 1, c->err, sizeof c->err);
@@ -577,6 +601,7 @@ int flake_encode_init(FlakeContext *s)
     memset(c->frame_buffer, 0, c->frame_buffer_size);
     c->frame_count = 0;
     c->last_frame = 0;
+    c->min_frame_size = 0xffffffffu;
     return header_len;
 }
 
@@ -586,10 +611,9 @@ void *flake_get_buffer(const FlakeContext *s)
     return ((FbCtx *)s->private_ctx)->frame_buffer;
 }
 
-void flake_encode_close(FlakeContext *s)
+static void flake_encode_close_impl(FlakeContext *s)
 {
     if (!s || !s->private_ctx) return;
-    ctx_bind_device((FbCtx *)s->private_ctx);
     ctx_free((FbCtx *)s->private_ctx);
     free(s->header);
     s->header = NULL;
@@ -600,6 +624,7 @@ void flake_encode_close(FlakeContext *s)
 static void account(FbCtx *c, const FbSummary *sm, uint64_t nsamples)
 {
     if ((int)sm->max_frame_bytes > c->max_frame_size) c->max_frame_size = (int)sm->max_frame_bytes;
+    if (sm->nframes && ~sm->min_frame_inv < c->min_frame_size) c->min_frame_size = ~sm->min_frame_inv;
     if (c->params.allow_vbs) c->frame_count += (uint32_t)nsamples;
     else c->frame_count += sm->nframes;
     c->stats.frames += sm->nframes;
@@ -612,14 +637,13 @@ static void account(FbCtx *c, const FbSummary *sm, uint64_t nsamples)
 /* ------------------------------------------------------------------ */
 /* flake_encode_frame -- encode.c:979-1008                              */
 /* ------------------------------------------------------------------ */
-int flake_encode_frame(FlakeContext *s, const int *samples, int block_size)
+static int flake_encode_frame_impl(FlakeContext *s, const int *samples, int block_size)
 {
     if (!s || !samples || !s->private_ctx) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
     if (block_size < 1 || block_size > c->params.block_size) return -1;
     if (c->last_frame) return -1;
     if (!c->params.allow_vbs && block_size != c->params.block_size) c->last_frame = 1;
-    ctx_bind_device(c);
 
     if (lane_submit(c, c->eng1, &c->one, samples, FLAKE_B200_PCM_S32, (uint64_t)block_size, c->frame_count))
         return -1;
@@ -713,11 +737,10 @@ static int default_chunk_blocks(const FbCtx *c, unsigned int stream_samples, uin
     return fb_chunk_blocks_for(c->device, c->params.block_size, c->channels, stream_samples, target_ints);
 }
 
-int flake_b200_set_chunk_blocks(FlakeContext *s, int blocks)
+static int flake_b200_set_chunk_blocks_impl(FlakeContext *s, int blocks)
 {
     if (!s || !s->private_ctx || blocks < 1) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    ctx_bind_device(c);
     if (c->engN && blocks != c->chunk_blocks) {
         fb_cuda_stream_sync(c->st);
         lane_free(&c->lane[0]); lane_free(&c->lane[1]);
@@ -741,7 +764,9 @@ static int ensure_batch_engine(FbCtx *c)
         c->engN = fb_engine_create(&c->cfg, c->device, (uint32_t)c->chunk_blocks, c->err, sizeof c->err);
         if (!c->engN) return -3;
     }
+    /* lane_alloc starts from a zeroed lane: never called on a live one (lanes_ready guards) */
     if (lane_alloc(&c->lane[0], c->engN, &c->cfg, NULL) || lane_alloc(&c->lane[1], c->engN, &c->cfg, NULL)) {
+        lane_free(&c->lane[0]); lane_free(&c->lane[1]);          /* whichever half was allocated */
         snprintf(c->err, sizeof c->err, "CUDA allocation of the batch lanes failed");
         return -3;
     }
@@ -760,7 +785,7 @@ unsigned long long flake_b200_max_encoded_size(const FlakeContext *s, unsigned l
     return frames * 96ull + ((nsamples * (unsigned long long)(s->channels * s->bits_per_sample + 1) + 7) >> 3) + 64;
 }
 
-long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
+static long long flake_b200_encode_stream_impl(FlakeContext *s, const void *pcm, int fmt,
                                    unsigned long long nsamples, unsigned char *out,
                                    unsigned long long out_cap, unsigned int *frame_len,
                                    unsigned int *frame_bs, unsigned int frame_cap,
@@ -768,7 +793,6 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
 {
     if (!s || !s->private_ctx || !pcm || !out) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    ctx_bind_device(c);
     if (fmt < FLAKE_B200_PCM_S32 || fmt > FLAKE_B200_PCM_S8) return -1;
     if (nframes_out) *nframes_out = 0;
     if (nsamples == 0) return 0;
@@ -804,6 +828,7 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
     uint32_t counter = c->frame_count;
     const uint32_t counter0 = c->frame_count;
     const int max0 = c->max_frame_size;
+    const uint32_t min0 = c->min_frame_size;
     const FlakeB200Stats stats0 = c->stats;
     int err = 0;
     int32_t *widen = NULL;          /* only for packed input in a container != ceil(bps/8) */
@@ -895,6 +920,7 @@ long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt,
         c->md5 = md5_backup;
         c->frame_count = counter0;
         c->max_frame_size = max0;
+        c->min_frame_size = min0;
         c->stats = stats0;
         return err;
     }
@@ -920,6 +946,7 @@ int flake_b200_reset_stream(FlakeContext *s)
     FbCtx *c = (FbCtx *)s->private_ctx;
     c->frame_count = 0;
     c->last_frame = 0;
+    c->min_frame_size = 0xffffffffu;
     fb_md5_init(&c->md5);
     c->max_frame_size = fb_verbatim_bound(&c->cfg);
     memset(&c->stats, 0, sizeof c->stats);
@@ -932,12 +959,11 @@ unsigned int flake_b200_tell(const FlakeContext *s)
     return ((const FbCtx *)s->private_ctx)->frame_count;
 }
 
-int flake_b200_device_capacity(FlakeContext *s, unsigned long long *max_samples,
+static int flake_b200_device_capacity_impl(FlakeContext *s, unsigned long long *max_samples,
                                unsigned long long *out_bytes, unsigned int *max_frames)
 {
     if (!s || !s->private_ctx) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    ctx_bind_device(c);
     if (!c->engD) {
         c->engD = fb_engine_create(&c->cfg, c->device, (uint32_t)c->dev_chunk_blocks, c->err, sizeof c->err);
         if (!c->engD) return -3;
@@ -985,13 +1011,19 @@ int flake_b200_stage_times(FlakeContext *s, double *ms, unsigned long long *laun
     return n;
 }
 
+int flake_b200_set_streaminfo_sizes(FlakeContext *s, int on)
+{
+    if (!s || !s->private_ctx) return -1;
+    ((FbCtx *)s->private_ctx)->report_min_frame = on ? 1 : 0;
+    return 0;
+}
+
 unsigned int flake_b200_subframe_record_size(void) { return (unsigned int)sizeof(FbSub); }
 
-int flake_b200_last_subframes(FlakeContext *s, void *subs, unsigned int max)
+static int flake_b200_last_subframes_impl(FlakeContext *s, void *subs, unsigned int max)
 {
     if (!s || !s->private_ctx || !subs) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    ctx_bind_device(c);
     FbEngine *e = c->last_engine ? c->last_engine : c->eng1;
     return fb_engine_read_subframes(e, (FbSub *)subs, max, c->st);
 }
@@ -1036,4 +1068,71 @@ const char *flake_b200_last_error(const FlakeContext *s)
 {
     if (!s || !s->private_ctx) return "no context";
     return ((const FbCtx *)s->private_ctx)->err;
+}
+
+/* ------------------------------------------------------------------ */
+/* entry points that touch the device: bind the context's device, restore the caller's */
+/* ------------------------------------------------------------------ */
+void flake_encode_close(FlakeContext *s)
+{
+    if (!s || !s->private_ctx) return;
+    const int prev = ctx_bind_device((const FbCtx *)s->private_ctx);
+    flake_encode_close_impl(s);
+    ctx_unbind_device(prev);
+}
+
+int flake_encode_frame(FlakeContext *s, const int *samples, int block_size)
+{
+    if (!s || !samples || !s->private_ctx) return -1;
+    const int prev = ctx_bind_device((const FbCtx *)s->private_ctx);
+    const int r = flake_encode_frame_impl(s, samples, block_size);
+    ctx_unbind_device(prev);
+    return r;
+}
+
+int flake_b200_set_chunk_blocks(FlakeContext *s, int blocks)
+{
+    if (!s || !s->private_ctx || blocks < 1) return -1;
+    const int prev = ctx_bind_device((const FbCtx *)s->private_ctx);
+    const int r = flake_b200_set_chunk_blocks_impl(s, blocks);
+    ctx_unbind_device(prev);
+    return r;
+}
+
+long long flake_b200_encode_stream(FlakeContext *s, const void *pcm, int fmt, unsigned long long nsamples, unsigned char *out,
+                                   unsigned long long out_cap, unsigned int *frame_len, unsigned int *frame_bs,
+                                   unsigned int frame_cap, unsigned int *nframes_out)
+{
+    if (!s || !s->private_ctx || !pcm || !out) return -1;
+    const int prev = ctx_bind_device((const FbCtx *)s->private_ctx);
+    const long long r = flake_b200_encode_stream_impl(s, pcm, fmt, nsamples, out, out_cap, frame_len, frame_bs, frame_cap, nframes_out);
+    ctx_unbind_device(prev);
+    return r;
+}
+
+int flake_b200_device_capacity(FlakeContext *s, unsigned long long *max_samples, unsigned long long *out_bytes,
+                               unsigned int *max_frames)
+{
+    if (!s || !s->private_ctx) return -1;
+    const int prev = ctx_bind_device((const FbCtx *)s->private_ctx);
+    const int r = flake_b200_device_capacity_impl(s, max_samples, out_bytes, max_frames);
+    ctx_unbind_device(prev);
+    return r;
+}
+
+int flake_b200_last_subframes(FlakeContext *s, void *subs, unsigned int max)
+{
+    if (!s || !s->private_ctx || !subs) return -1;
+    const int prev = ctx_bind_device((const FbCtx *)s->private_ctx);
+    const int r = flake_b200_last_subframes_impl(s, subs, max);
+    ctx_unbind_device(prev);
+    return r;
+}
+
+int flake_encode_init(FlakeContext *s)
+{
+    const int prev = fb_cuda_current_device();      /* engine creation selects the context's device */
+    const int r = flake_encode_init_impl(s);
+    if (prev >= 0 && fb_cuda_current_device() != prev) fb_cuda_set_device(prev);
+    return r;
 }

@@ -542,6 +542,7 @@ k_pack(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const void 
         frame_off[f] = off;
         if (frame_bs) frame_bs[f] = (uint32_t)n;
         atomicMax(&summary->max_frame_bytes, nbytes);
+        atomicMax(&summary->min_frame_inv, ~nbytes);              /* min over the frames, kept as a max */
         if (verbatim) {
             atomicAdd(&summary->verbatim_frames, 1u);
             for (int c = 0; c < C; c++) subs[(size_t)f * C + c].type = 1;

@@ -51,8 +51,12 @@ typedef struct FlakeB200Stats {
 /* Select the CUDA device used by contexts initialised afterwards (default:
  * $FLAKE_B200_DEVICE, else the current device).  Returns 0 or -1. */
 FLAKE_API int flake_b200_set_device(int device);
+/* The same for contexts initialised BY THE CALLING THREAD only (takes precedence over the process
+ * default; -1 clears it): threads that each drive a GPU of their own need no shared state. */
+FLAKE_API int flake_b200_set_thread_device(int device);
 
-/* Blocks per engine pass of the batch calls (default $FLAKE_B200_CHUNK_BLOCKS or 2048). */
+/* Blocks per engine pass of the batch calls (default: $FLAKE_B200_CHUNK_BLOCKS, else a multiple of
+ * the device's SM count near 80 Mi channel-samples for host buffers, 320 Mi for device-resident input). */
 FLAKE_API int flake_b200_set_chunk_blocks(FlakeContext *s, int blocks);
 
 /*
@@ -98,7 +102,9 @@ FLAKE_API int flake_b200_reset_stream(FlakeContext *s);
  * and the call returns without synchronising.  At most
  * flake_b200_device_capacity() samples per call.  `d_summary` receives
  * {uint32 nframes, uint32 max_frame_bytes, uint64 total_bytes, uint32
- * verbatim_frames, uint32 0}.  Does not touch the context's MD5 or counters:
+ * verbatim_frames, uint32 ~min_frame_bytes}.  Passes of one context share scratch buffers and
+ * are therefore serial: a call on another stream than the previous one is made to wait for it
+ * (stream-ordered, no host synchronisation).  Does not touch the context's MD5 or counters:
  * `first_number` is the header number of the first frame.
  * Returns 0 or a negative error.
  */
@@ -119,7 +125,8 @@ FLAKE_API int flake_b200_last_subframes(FlakeContext *s, void *subs, unsigned in
 FLAKE_API unsigned int flake_b200_subframe_record_size(void);
 
 /*
- * Per-stage device timing of the batch/device engine, measured with CUDA events
+ * Per-stage device timing of the DEVICE-RESIDENT engine (flake_b200_encode_device; the host-buffer
+ * calls run on engines of their own and are not instrumented), measured with CUDA events
  * recorded between the kernels on the launching stream.  Five stages:
  * 0 frame table (+VBS split), 1 prepare, 2 LPC analysis, 3 order/Rice search,
  * 4 pack (bits, CRCs, frame offsets, frames written back to back).
@@ -182,13 +189,14 @@ typedef struct FlakeB200CorpusStream {
     long long bytes;                    /* frame bytes written, or a negative error              */
     unsigned int nframes;
     unsigned int max_frame_size;
+    unsigned int min_frame_size;        /* smallest frame (the reference's STREAMINFO keeps 0)   */
     unsigned int verbatim_frames;
     unsigned char md5sum[16];
 } FlakeB200CorpusStream;
 
 typedef struct FlakeB200CorpusOptions {
     int threads_per_device;             /* GPU worker threads per device, 0 = default (2)        */
-    int md5_threads;                    /* 0 = one per online CPU (never more than streams)      */
+    int md5_threads;                    /* most MD5 workers; 0 = online CPUs minus the GPU workers */
     int chunk_blocks;                   /* blocks per engine pass, 0 = default                   */
 } FlakeB200CorpusOptions;
 
@@ -226,6 +234,11 @@ FLAKE_API const char *flake_b200_corpus_error(const FlakeB200Corpus *corpus);
  * length needed when data == NULL, or -1. */
 FLAKE_API int flake_b200_corpus_stream_header(const FlakeContext *proto, const FlakeB200CorpusStream *stream,
                                               unsigned char *data, unsigned int cap);
+
+/* STREAMINFO's minimum frame size: the reference always writes 0 = unknown (metadata.c:52), and
+ * so does this library unless switched on here; then flake_get_streaminfo reports the smallest
+ * frame encoded so far.  Not part of the byte-identical stream. */
+FLAKE_API int flake_b200_set_streaminfo_sizes(FlakeContext *s, int on);
 
 FLAKE_API int flake_b200_get_stats(const FlakeContext *s, FlakeB200Stats *stats);
 FLAKE_API const char *flake_b200_last_error(const FlakeContext *s);

@@ -169,3 +169,28 @@ def test_seektable_from_frame_lengths(lib):
         got = lib.flake_b200_write_seektable(flen.ctypes.data, fbs.ctypes.data, len(flen), interval, buf, need)
         assert got == need and bytes(buf) == want
         assert lib.flake_b200_write_seektable(flen.ctypes.data, fbs.ctypes.data, len(flen), interval, buf, need - 1) == -1
+
+
+def test_reference_callers_link_against_the_library():
+    """north_star: "the flake CLI and util/api_example.c link against it unchanged".  build()
+    compiles the reference's own flake/flake.c (+ libpcm_io) and util/api_example.c, unchanged,
+    against include/flake.h and links them with flake_b200/lib/libflake.so, plus the CLI with
+    patches/flake_cli_batch.patch applied (oracle/Makefile).  Here: they exist, every libflake
+    symbol they import is exported by the library, and the dynamic loader resolves them (ldd)."""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    exes = [os.path.join(ref, n) for n in ("flake_cli_b200", "flake_cli_b200_batch", "api_example_b200")]
+    if not all(os.path.exists(e) for e in exes):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    exported = set(l.split()[-1] for l in subprocess.run(
+        ["nm", "-D", "--defined-only", os.path.join(ROOT, "flake_b200", "lib", "libflake.so")],
+        stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines() if l.strip())
+    for e in exes:
+        und = [l.split()[-1] for l in subprocess.run(["nm", "-D", "-u", e], stdout=subprocess.PIPE, text=True,
+                                                     check=True).stdout.splitlines() if "flake_" in l]
+        assert und, e
+        assert set(und) <= exported, (e, sorted(set(und) - exported))
+        ldd = subprocess.run(["ldd", e], stdout=subprocess.PIPE, text=True).stdout
+        assert "libflake.so" in ldd and "libflake.so => not found" not in ldd, ldd
+    und = subprocess.run(["nm", "-D", "-u", exes[1]], stdout=subprocess.PIPE, text=True).stdout
+    assert "flake_b200_encode_stream" in und and "flake_encode_frame" not in und

@@ -154,6 +154,34 @@ def test_unmodified_reference_cli_links_and_matches(gpu_lib, oracle, tmp_path):
         assert a.read_bytes() == b.read_bytes()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("bps", [16, 24])
+def test_patched_cli_batch_path_matches_reference_cli(gpu_lib, oracle, tmp_path, bps):
+    """oracle/_ref/flake_cli_b200_batch = flake/flake.c with patches/flake_cli_batch.patch (the loop
+    over flake_encode_frame replaced by flake_b200_encode_stream on 2048-block batches), linked
+    against libflake.so: byte-identical files to the reference CLI, every level, s16 and s24 WAV,
+    batches that end inside the stream and a short last block."""
+    import subprocess
+    from oracle import pyoracle
+    cli = os.path.join(os.path.dirname(pyoracle.REF_SO), "flake_cli_b200_batch")
+    if not os.path.exists(cli) or not os.path.exists(pyoracle.REF_CLI):
+        pytest.skip("oracle/_ref CLIs not built (needs /root/reference at build time)")
+    rate = 44100 if bps == 16 else 96000
+    pcm = synth.synth_pcm(4096 * 9 + 1777, 2, bps, rate, seed=40 + bps)
+    wav = tmp_path / "in.wav"
+    wav.write_bytes(synth.wav_bytes(pcm, bps, rate))
+    env = dict(os.environ, FLAKE_B200_BATCH_BLOCKS="4")      # three batches + the short block
+    for level in ("-0", "-5", "-8", "-9", "-12"):
+        a, b = tmp_path / "a.flac", tmp_path / "b.flac"
+        subprocess.run([cli, "-q", level, str(wav), "-o", str(a)], check=True, env=env)
+        subprocess.run([pyoracle.REF_CLI, "-q", level, str(wav), "-o", str(b)], check=True)
+        assert a.read_bytes() == b.read_bytes(), level
+    a, b = tmp_path / "a.flac", tmp_path / "b.flac"
+    subprocess.run([cli, "-q", "-8", str(wav), "-o", str(a)], check=True)          # default batch size: one call
+    subprocess.run([pyoracle.REF_CLI, "-q", "-8", str(wav), "-o", str(b)], check=True)
+    assert a.read_bytes() == b.read_bytes()
+
+
 def test_plain_c_caller(gpu_lib, oracle, tmp_path):
     """tests/c/batch_example.c: a C program in the shape of util/api_example.c, compiled against
     include/*.h and linked with libflake.so; per-block and batch outputs must be one valid file."""

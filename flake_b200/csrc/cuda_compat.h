@@ -79,6 +79,13 @@ __device__ __forceinline__ void fb_mbar_wait(fb_mbar_t *bar, unsigned parity)
 }
 #endif
 
+/* 2^-s as a double, 0 <= s < 1023 */
+#ifdef FLAKE_B200_CUDA_EMU
+static inline double fb_exp2_neg(int s) { return ldexp(1.0, -s); }
+#else
+__device__ __forceinline__ double fb_exp2_neg(int s) { return __hiloint2double((1023 - s) << 20, 0); }
+#endif
+
 /* marks a block as not speculatable, so that a rarely taken `if` stays a branch instead of
  * being turned into selects executed by every thread */
 #ifdef FLAKE_B200_CUDA_EMU

@@ -56,12 +56,24 @@ __device__ unsigned long long g_sprof[16];
 #define FB_PROF_PASS
 #endif
 
+#define FB_F64_MAGIC 6755399441055744.0          /* 1.5 * 2^52 */
+/* Which kernel takes the FP64 bodies.  Measured (ms per pass, search stage): the order-32 kernel
+ * is bound by the multiplies (C3, exhaustive search over 32 orders: 10.74 with IMAD.WIDE, 8.25
+ * with DFMA); the order <= 12 kernel is bound by barriers and latency, not by the multiply pipe,
+ * and the int -> double conversions of the window only add to its critical path (C2 3.21 -> 4.09,
+ * C4 4.00 -> 4.25), so it keeps IMAD.WIDE. */
+#ifndef FB_F64_WIDE
+#define FB_F64_WIDE(MAXP) ((MAXP) > 12)
+#endif
+
 template <int MAXP>
 struct FbSearchShared {
     unsigned long long sums[256];   /* finest-level partition sums when runs do not tile the partitions */
     uint8_t  kbuf[FB_GROUP_OF(MAXP)][512];   /* group member: parameter of partition j at level L at [(1<<L)-1+j] */
     uint8_t  kbest[256];            /* best candidate so far: parameters at its partition order */
     int32_t  coef[MAXP][MAXP];      /* candidate rows (row = order-1), zero padded */
+    double   coefd[FB_F64_WIDE(MAXP) ? MAXP : 1][FB_F64_WIDE(MAXP) ? MAXP : 1];   /* the same rows as coef * 2^-shift
+                                     * (exact), for the FP64 bodies (fb_floor_lo32); only where they are used */
     int32_t  shift[MAXP];
     uint32_t sumabs[MAXP];          /* sum |coef| per row */
     uint8_t  narrow_of[MAXP];       /* row can be costed in 32-bit arithmetic */
@@ -72,6 +84,21 @@ struct FbSearchShared {
     int32_t  best_porder, best_method;
     uint32_t best_bits;
 };
+
+/*
+ * The 64-bit predictor on the FP64 pipe.  Where 32-bit arithmetic cannot be proven exact (24-bit
+ * audio: |prediction| reaches 2^37) the reference's int64 sum costs an IMAD.WIDE per tap, a quarter
+ * rate instruction (32 lanes/clk/SM).  B200's DFMA runs at 64 lanes/clk/SM and is exact here:
+ * |coef| < 2^14, |sample| < 2^32, <= 32 taps, so every product and partial sum is an integer
+ * below 2^51 (times the power of two 2^-shift folded into the coefficients, which only moves the
+ * exponent).  floor(pred / 2^shift) -- the arithmetic right shift of optimize.c:84-118 -- is one
+ * add of 1.5 * 2^52 rounded toward minus infinity: the low mantissa word of the sum is the floor
+ * modulo 2^32, which is all the residual (an int32) keeps.
+ */
+__device__ __forceinline__ int32_t fb_floor_lo32(double y)
+{
+    return __double2loint(__dadd_rd(y, FB_F64_MAGIC));
+}
 
 /* optimize.c:34-68, one sample */
 __device__ __forceinline__ int32_t fb_fixed_residual(const int32_t *x, int i, int order)
@@ -458,18 +485,36 @@ __device__ __forceinline__ void fb_run_residual(FbSearchShared<MAXP> &S, const i
 
     /* residuals of the run, branch free */
     int32_t r[FB_RUN];
+    if constexpr (WIDE && FB_F64_WIDE(MAXP)) {
+        /* the 64-bit prediction on the FP64 pipe, see fb_floor_lo32 */
+        const double *cd = S.coefd[row];
+        double wd[P + FB_RUN - 1], pd[FB_RUN];
 #pragma unroll
-    for (int k = 0; k < FB_RUN; k++) {
-        if (WIDE) {
-            long long pred = 0;
+        for (int q = 0; q < P + FB_RUN - 1; q++) wd[q] = (double)w[q];
 #pragma unroll
-            for (int j = 0; j < P; j++) pred += (long long)c[j] * (long long)w[P + k - 1 - j];
-            r[k] = (int32_t)((long long)w[P + k] - (pred >> shift));
-        } else {
-            int32_t pred = 0;
+        for (int k = 0; k < FB_RUN; k++) pd[k] = 0.0;
 #pragma unroll
-            for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
-            r[k] = w[P + k] - (pred >> shift);
+        for (int j = 0; j < P; j++) {
+            const double cj = cd[j];
+#pragma unroll
+            for (int k = 0; k < FB_RUN; k++) pd[k] = __fma_rn(cj, wd[P + k - 1 - j], pd[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < FB_RUN; k++) r[k] = (int32_t)((uint32_t)w[P + k] - (uint32_t)fb_floor_lo32(pd[k]));
+    } else {
+#pragma unroll
+        for (int k = 0; k < FB_RUN; k++) {
+            if (WIDE) {
+                long long pred = 0;
+#pragma unroll
+                for (int j = 0; j < P; j++) pred += (long long)c[j] * (long long)w[P + k - 1 - j];
+                r[k] = (int32_t)((long long)w[P + k] - (pred >> shift));
+            } else {
+                int32_t pred = 0;
+#pragma unroll
+                for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
+                r[k] = w[P + k] - (pred >> shift);
+            }
         }
     }
     /* zig-zag sum of the run (rice.c:76-95) */
@@ -605,42 +650,71 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
         const fb_sptr xr = fb_to_sptr(xs);
 #endif
         FbWindow<P, (P + FB_RUN) / 4>::load(xr, i0 + FB_HIST, w);
+        if constexpr (WIDE && FB_F64_WIDE(MAXP)) {
+            /* FP64 bodies: the window is converted once for all members of the group */
+            double wd[P + FB_RUN - 1];
+#pragma unroll
+            for (int q = 0; q < P + FB_RUN - 1; q++) wd[q] = (double)w[q];
 #pragma unroll 1
-        for (int m = 0; m < count; m++) {
-            const int order = fb_order_of(ord, m), row = is_lpc ? order - 1 : order;
-            int32_t c[P];
+            for (int m = 0; m < count; m++) {
+                const int order = fb_order_of(ord, m), row = is_lpc ? order - 1 : order;
+                const double *cd = S.coefd[row];
+                double pd[FB_RUN];
 #pragma unroll
-            for (int g = 0; g < P / 4; g++) {
-                const int4 v = *reinterpret_cast<const int4 *>(&S.coef[row][4 * g]);
-                c[4 * g] = v.x; c[4 * g + 1] = v.y; c[4 * g + 2] = v.z; c[4 * g + 3] = v.w;
-            }
-            const int shift = S.shift[row];
-            unsigned long long acc = 0;
-            uint32_t a32 = 0;
-            const int wlim = order - i0;                          /* samples of this run below the order */
+                for (int k = 0; k < FB_RUN; k++) pd[k] = 0.0;
 #pragma unroll
-            for (int k = 0; k < FB_RUN; k++) {
-                if (WIDE) {
-                    long long pred = 0;
+                for (int j = 0; j < P; j++) {
+                    const double cj = cd[j];
 #pragma unroll
-                    for (int j = 0; j < P; j++) pred += (long long)c[j] * (long long)w[P + k - 1 - j];
-                    const int32_t rk = (int32_t)((long long)w[P + k] - (pred >> shift));
-                    acc += fb_zigzag(rk);
-                    if (k < P && k < wlim) acc -= fb_zigzag(rk);       /* warm-up samples are not counted */
-                } else {
-                    int32_t pred = 0;
-#pragma unroll
-                    for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
-                    /* zigzag(r) = (|4r + 1| - 1) / 2, |r| < 2^26: the sum of sixteen |4r + 1| fits 32 bits;
-                     * |x| + acc is one instruction (VABSDIFF); a warm-up sample (order <= P) counts as r = 0.
-                     * (Measured and dropped: the warm-up runs costed apart by sixteen threads per run so
-                     * that this body does not know the case, 3.58 vs 3.16 ms.) */
-                    int32_t rk = w[P + k] - (pred >> shift);
-                    if (k < P && k < wlim) rk = 0;
-                    a32 = __sad(4 * rk + 1, 0, a32);
+                    for (int k = 0; k < FB_RUN; k++) pd[k] = __fma_rn(cj, wd[P + k - 1 - j], pd[k]);
                 }
+                const int wlim = order - i0;                      /* samples of this run below the order */
+                unsigned long long acc = 0;
+#pragma unroll
+                for (int k = 0; k < FB_RUN; k++) {
+                    const int32_t rk = (int32_t)((uint32_t)w[P + k] - (uint32_t)fb_floor_lo32(pd[k]));
+                    if (!(k < P && k < wlim)) acc += fb_zigzag(rk);  /* warm-up samples are not counted */
+                }
+                runsum0[m * rstride + i0 / FB_RUN] = acc;
             }
-            runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)((a32 - FB_RUN) >> 1);
+        } else {
+#pragma unroll 1
+            for (int m = 0; m < count; m++) {
+                const int order = fb_order_of(ord, m), row = is_lpc ? order - 1 : order;
+                int32_t c[P];
+#pragma unroll
+                for (int g = 0; g < P / 4; g++) {
+                    const int4 v = *reinterpret_cast<const int4 *>(&S.coef[row][4 * g]);
+                    c[4 * g] = v.x; c[4 * g + 1] = v.y; c[4 * g + 2] = v.z; c[4 * g + 3] = v.w;
+                }
+                const int shift = S.shift[row];
+                const int wlim = order - i0;                      /* samples of this run below the order */
+                unsigned long long acc = 0;
+                uint32_t a32 = 0;
+#pragma unroll
+                for (int k = 0; k < FB_RUN; k++) {
+                    if (WIDE) {
+                        long long pred = 0;
+#pragma unroll
+                        for (int j = 0; j < P; j++) pred += (long long)c[j] * (long long)w[P + k - 1 - j];
+                        const int32_t rk = (int32_t)((long long)w[P + k] - (pred >> shift));
+                        acc += fb_zigzag(rk);
+                        if (k < P && k < wlim) acc -= fb_zigzag(rk);       /* warm-up samples are not counted */
+                    } else {
+                        int32_t pred = 0;
+#pragma unroll
+                        for (int j = 0; j < P; j++) pred += c[j] * w[P + k - 1 - j];
+                        /* zigzag(r) = (|4r + 1| - 1) / 2, |r| < 2^26: the sum of sixteen |4r + 1| fits 32 bits;
+                         * |x| + acc is one instruction (VABSDIFF); a warm-up sample (order <= P) counts as r = 0.
+                         * (Measured and dropped: the warm-up runs costed apart by sixteen threads per run so
+                         * that this body does not know the case, 3.58 vs 3.16 ms.) */
+                        int32_t rk = w[P + k] - (pred >> shift);
+                        if (k < P && k < wlim) rk = 0;
+                        a32 = __sad(4 * rk + 1, 0, a32);
+                    }
+                }
+                runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)((a32 - FB_RUN) >> 1);
+            }
         }
     }
 }
@@ -839,7 +913,10 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
         if (tid < 5) {
             const int32_t bc[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
             const uint32_t sa[5] = {0, 1, 3, 7, 15};
-            for (int j = 0; j < MAXP; j++) S.coef[tid][j] = j < 4 ? bc[tid][j] : 0;   /* bodies may cover more taps */
+            for (int j = 0; j < MAXP; j++) {                 /* bodies may cover more taps */
+                S.coef[tid][j] = j < 4 ? bc[tid][j] : 0;
+                if (FB_F64_WIDE(MAXP)) S.coefd[tid][j] = j < 4 ? (double)bc[tid][j] : 0.0;
+            }
             S.shift[tid] = 0;
             S.sumabs[tid] = sa[tid];
             const unsigned long long rb = (unsigned long long)sb_maxabs + (unsigned long long)sa[tid] * sb_maxabs + 1ull;
@@ -932,6 +1009,12 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
             S.narrow_of[rowi] = pm < 0x80000000ull && rb < (1ull << 26);
             S.sum32_of[rowi] = 2ull * rb * (unsigned long long)n < 0x80000000ull;   /* zig-zag <= 2 rb: every partition sum < 2^31 */
         }
+        /* the rows for the FP64 bodies: coefficient * 2^-shift, exact */
+        if (FB_F64_WIDE(MAXP))
+            for (int e = tid; e < MAXP * MAXP; e += T) {
+                const int rowi = e / MAXP, j = e % MAXP;
+                S.coefd[rowi][j] = (double)S.coef[rowi][j] * fb_exp2_neg(S.shift[rowi]);
+            }
         __syncthreads();
     }
     FB_PROF(0);

@@ -24,6 +24,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <fenv.h>
 #include <functional>
 #include <vector>
 #include <algorithm>
@@ -294,6 +295,18 @@ inline unsigned max(int a, unsigned b) { return (unsigned)a > b ? (unsigned)a : 
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+/* a + b rounded toward minus infinity */
+inline double __dadd_rd(double a, double b)
+{
+    const int old = fegetround();
+    fesetround(FE_DOWNWARD);
+    volatile double x = a, y = b;
+    volatile double r = x + y;
+    fesetround(old);
+    return r;
+}
+inline int __double2loint(double d) { uint64_t u; memcpy(&u, &d, 8); return (int)(uint32_t)u; }
 inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 inline double __int2double_rn(int v) { return (double)v; }
 inline int __double2int_rz(double x)

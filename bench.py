@@ -534,6 +534,14 @@ def run_gpu_arm(args):
     e2e_value = world * nsamples / (e2e_ms_max * 1e-3) / 1e6
     single_out = h_out[:e2e_bytes].numpy().copy() if rank == 0 else None     # for the parity leg below
 
+    # ---- the per-block API (what the unmodified CLI calls): one synchronous call per block ---
+    per_block = None
+    if rank == 0 and not os.environ.get("FLAKE_BENCH_SKIP_PER_BLOCK"):
+        try:
+            per_block = per_block_leg(lib, api, pcm_np)
+        except Exception as exc:
+            per_block = {"value": None, "error": str(exc)[:200]}
+
     # ---- e2e: the fixed corpus through flake_b200_encode_corpus, split over the ranks ------
     del h_out, h_pcm32, pcm_pinned
     corpus_rec = run_corpus_leg(lib, api, torch, dist, rank, world, local, host_group, allmax, barrier,
@@ -614,6 +622,7 @@ def run_gpu_arm(args):
             "md5_thread_ms": round(e2e_stats.md5_ms, 1),
             "gpu_ms": round(e2e_stats.gpu_ms, 1),
             "wall": "one stream's MD5 is a serial chain on one host core (md5_thread_ms of ms_per_step)"},
+        "per_block_api": per_block,
         "parity": parity,
         "gpu_launches": launches,
         "clocks": clk,
@@ -666,6 +675,32 @@ def run_other_config(lib, name, dev, stream, peak_gbs, peak_src, traffic, torch)
     except Exception as exc:
         rec["parity"] = {"frames_compared": 0, "error": str(exc)[:300]}
     return rec
+
+
+def per_block_leg(lib, api, pcm_i32, nblocks=1500):
+    """flake_encode_frame in a loop, one 4096-sample block per synchronous call (encode.c:979-1008,
+    flake/flake.c:624-663): what a caller that links the library without the batch calls gets.
+    Latency bound: upload, five launches, two waits and the download of one block per call."""
+    enc = api.Encoder(lib, CHANNELS, RATE, BPS, nblocks * BLOCK, LEVEL)
+    enc.init()
+    ctx = C.byref(enc.ctx)
+    pcm = np.ascontiguousarray(pcm_i32[:nblocks * BLOCK], dtype=np.int32)
+    base, step = pcm.ctypes.data, BLOCK * CHANNELS * 4
+    for b in range(50):
+        lib.flake_encode_frame(ctx, base + b * step, BLOCK)
+    lib.flake_b200_reset_stream(ctx)
+    t0 = time.perf_counter()
+    nbytes = 0
+    for b in range(nblocks):
+        fs = lib.flake_encode_frame(ctx, base + b * step, BLOCK)
+        if fs <= 0:
+            raise RuntimeError("flake_encode_frame returned %d" % fs)
+        nbytes += fs
+    dt = time.perf_counter() - t0
+    enc.close()
+    return {"value": round(nblocks * BLOCK / dt / 1e6, 2), "unit": "MSamples/s", "us_per_call": round(dt / nblocks * 1e6, 1),
+            "blocks": nblocks, "bytes": nbytes,
+            "note": "one block per synchronous flake_encode_frame call; the batch calls exist because of this"}
 
 
 def pcie_probe(torch, dev, nbytes=1 << 30):

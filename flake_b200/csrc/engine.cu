@@ -243,8 +243,9 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     /* The attribute is per function, per device and per PROCESS, not per engine: every engine sets
      * the same constant (the staging budget), so a later engine with smaller blocks can never
      * lower it under a live engine's launch size. */
-    cudaFuncSetAttribute(k_search<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
-    cudaFuncSetAttribute(k_search<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_search<12, FB_SEARCH_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_search<12, FB_SEARCH_CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_search<32, FB_SEARCH_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
     cudaFuncSetAttribute(k_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { set_err(err, errlen, "cudaFuncSetAttribute failed", ce); fb_engine_destroy(e); return nullptr; }
@@ -383,16 +384,19 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
         e->launches += 1;
     }
     FB_MARK(3);
-    if (cfg.prediction_type == 2 && cfg.max_order > 12) {
-        FB_LAUNCH(k_search<32>, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
-                  cfg, e->d_frames, e->d_nframes, d_pcm, fmt, pcm_bytes, e->d_modes, e->d_smp, e->d_res, e->d_subs,
-                  e->d_coefs, e->d_shifts, e->d_plan, e->search_smem_ints);
-    } else {
-        FB_LAUNCH(k_search<12>, dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st,
-                  cfg, e->d_frames, e->d_nframes, d_pcm, fmt, pcm_bytes, e->d_modes, e->d_smp, e->d_res, e->d_subs,
-                  e->d_coefs, e->d_shifts, e->d_plan, e->search_smem_ints);
-    }
-    FB_LAUNCHED(cfg.prediction_type == 2 && cfg.max_order > 12 ? "k_search<32>" : "k_search<12>");
+    /* the CD-audio shape of presets 8, 9 (and 11 with longer predictors) has an instantiation of
+     * its own: less code to fetch (k_search.cuh, FB_SEARCH_CD) */
+    const bool cd_shape = cfg.channels == 2 && fmt == FB_PCM_S16LE && cfg.prediction_type == 2 && cfg.order_method == 6;
+    const char *search_name;
+#define FB_SEARCH_GO(MAXP_, SPEC_)                                                                              \
+        FB_LAUNCH((k_search<MAXP_, SPEC_>), dim3(grid_subs), dim3(FB_SEARCH_THREADS), (size_t)e->search_smem_ints * 4, st, \
+                  cfg, e->d_frames, e->d_nframes, d_pcm, fmt, pcm_bytes, e->d_modes, e->d_smp, e->d_res, e->d_subs,     \
+                  e->d_coefs, e->d_shifts, e->d_plan, e->search_smem_ints)
+    if (cfg.prediction_type == 2 && cfg.max_order > 12) { search_name = "k_search<32>"; FB_SEARCH_GO(32, FB_SEARCH_ANY); }
+    else if (cd_shape) { search_name = "k_search<12, CD>"; FB_SEARCH_GO(12, FB_SEARCH_CD); }
+    else { search_name = "k_search<12>"; FB_SEARCH_GO(12, FB_SEARCH_ANY); }
+#undef FB_SEARCH_GO
+    FB_LAUNCHED(search_name);
     FB_MARK(4);
     /* threads per frame by the work in it (measured: 8192 samples per frame 1.75 ms with 128 threads vs
      * 1.88 with 256 per C2 stream; 32768 samples per frame 2.79 vs 2.08) */

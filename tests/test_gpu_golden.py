@@ -2,6 +2,7 @@
 at BASELINE.json sizes, through size-independent properties: encode -> decode round trip with
 every CRC-8 / CRC-16 and the STREAMINFO MD5 verified, frame accounting, per-block API ==
 batch API == frame-range-sharded encode."""
+import ctypes as C
 import hashlib
 import json
 import os
@@ -198,3 +199,56 @@ def test_plain_c_caller(gpu_lib, oracle, tmp_path):
     assert da == db
     dec, info = oracle.decode(da)
     assert info.md5_ok == 1 and info.decoded_samples == 4096 * 20 + 1234
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [8, 9])
+def test_seektable_and_frame_sizes_from_a_real_encode(gpu_lib, oracle, level):
+    """SEEKTABLE built from the frame lengths / block sizes the batch call returns
+    (level 9: variable block size, several frames per block), and STREAMINFO's opt-in minimum frame
+    size.  Every seek point must be the byte offset of a frame whose header carries the point's
+    sample number; the stream with the table inserted must still decode bit-exactly."""
+    import struct
+    ch, bps, rate = 2, 16, 44100
+    n = 4096 * 40 + 1000
+    pcm = synth.synth_pcm(n, ch, bps, rate, seed=11)
+    if level == 9:        # bursts that make the VBS splitter cut blocks, then the same short tail
+        pcm = np.concatenate([_vbs_pcm(4096 * 40, ch, bps, 13), pcm[4096 * 40:]])
+    enc = api.Encoder(gpu_lib, ch, rate, bps, n, level)
+    header = enc.init()
+    try:
+        assert gpu_lib.flake_b200_set_streaminfo_sizes(C.byref(enc.ctx), 1) == 0
+        data, flen, fbs = enc.encode_stream(pcm)
+        si, si_bytes = enc.streaminfo()
+    finally:
+        enc.close()
+    frames = data.tobytes()
+    assert si.min_frame_size == int(flen.min()) and si.max_frame_size >= int(flen.max())
+    interval = 10 * 4096
+    need = gpu_lib.flake_b200_write_seektable(flen.ctypes.data, fbs.ctypes.data, len(flen), interval, None, 0)
+    assert need > 0 and need % 18 == 0
+    buf = (C.c_ubyte * need)()
+    assert gpu_lib.flake_b200_write_seektable(flen.ctypes.data, fbs.ctypes.data, len(flen), interval, buf, need) == need
+    offs = np.concatenate([[0], np.cumsum(flen)]).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum(fbs)]).astype(np.int64)
+    pts = [struct.unpack(">QQH", bytes(buf)[i:i + 18]) for i in range(0, need, 18)]
+    assert pts[0][:2] == (0, 0) and len(pts) >= n // interval
+    for sample, off, count in pts:
+        f = int(np.searchsorted(starts, sample))
+        assert starts[f] == sample and offs[f] == off and fbs[f] == count          # a frame boundary, its size
+        assert frames[off] == 0xff and (frames[off + 1] & 0xfe) == 0xf8              # frame sync code
+    # the table as a metadata block (type 3) between STREAMINFO and the rest: still one valid stream
+    hdr = bytearray(header)
+    hdr[8:8 + 34] = si_bytes
+    with_table = bytes(hdr[:42]) + bytes([3]) + struct.pack(">I", need)[1:] + bytes(buf) + bytes(hdr[42:]) + frames
+    dec, info = oracle.decode(with_table)
+    assert info.md5_ok == 1 and np.array_equal(dec, pcm)
+
+
+def _vbs_pcm(n, ch, bps, seed):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.vbs_burst_pcm(n, ch, bps, seed, 4096)

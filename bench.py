@@ -77,6 +77,15 @@ E2E_TRACKS = 128
 E2E_TRACK_SAMPLES = 225 * RATE            # 3 min 45 s: 2423 blocks of 4096 (the last one short)
 
 
+def _jsonable(o):
+    """numpy scalars / arrays that found their way into the line"""
+    if isinstance(o, np.generic):
+        return o.item()
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    raise TypeError("not JSON serializable: %r" % type(o))
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -535,12 +544,12 @@ def run_gpu_arm(args):
     single_out = h_out[:e2e_bytes].numpy().copy() if rank == 0 else None     # for the parity leg below
 
     # ---- the per-block API (what the unmodified CLI calls): one synchronous call per block ---
-    per_block = None
+    per_block_rec = None
     if rank == 0 and not os.environ.get("FLAKE_BENCH_SKIP_PER_BLOCK"):
         try:
-            per_block = per_block_leg(lib, api, pcm_np)
+            per_block_rec = per_block_leg(lib, api, pcm_np)
         except Exception as exc:
-            per_block = {"value": None, "error": str(exc)[:200]}
+            per_block_rec = {"value": None, "error": str(exc)[:200]}
 
     # ---- e2e: the fixed corpus through flake_b200_encode_corpus, split over the ranks ------
     del h_out, h_pcm32, pcm_pinned
@@ -622,7 +631,7 @@ def run_gpu_arm(args):
             "md5_thread_ms": round(e2e_stats.md5_ms, 1),
             "gpu_ms": round(e2e_stats.gpu_ms, 1),
             "wall": "one stream's MD5 is a serial chain on one host core (md5_thread_ms of ms_per_step)"},
-        "per_block_api": per_block,
+        "per_block_api": per_block_rec,
         "parity": parity,
         "gpu_launches": launches,
         "clocks": clk,
@@ -634,7 +643,7 @@ def run_gpu_arm(args):
         "step_ms": [round(x, 2) for x in step_ms],
         "rank_ms_per_step": rank_ms,
     }
-    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    os.write(real_stdout, (json.dumps(line, default=_jsonable) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

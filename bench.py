@@ -730,6 +730,29 @@ def pcie_probe(torch, dev, nbytes=1 << 30):
     return out
 
 
+def host_read_probe(buf_u8: np.ndarray, threads: int, seconds: float = 0.25):
+    """Aggregate read rate of the host cores over `buf_u8` (GB/s): every thread sums its own slice
+    (numpy releases the GIL).  The e2e leg moves ~10 bytes of host DRAM traffic per sample (MD5
+    read + DMA read + DMA write), so this is the wall the box runs into as GPUs are added."""
+    view = buf_u8[:buf_u8.size // 8 * 8].view(np.uint64)
+    per = view.size // max(1, threads)
+    done = [0] * threads
+    stop = time.perf_counter() + seconds
+
+    def work(t):
+        sl = view[t * per:(t + 1) * per]
+        while time.perf_counter() < stop:
+            int(sl.sum())
+            done[t] += sl.nbytes
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    return round(sum(done) / (time.perf_counter() - t0) / 1e9, 1)
+
+
 def run_corpus_leg(lib, api, torch, dist, rank, world, local, host_group, allmax, barrier, steps):
     """e2e: the fixed corpus (E2E_TRACKS tracks, packed s16le in page-locked host memory) through
     flake_b200_encode_corpus.  Rank r takes tracks r, r + world, ...; one library call per step
@@ -809,6 +832,11 @@ def run_corpus_leg(lib, api, torch, dist, rank, world, local, host_group, allmax
             pcie = pcie_probe(torch, dev)
         except Exception:
             pass
+        host_gbs = None
+        try:
+            host_gbs = host_read_probe(in_np.reshape(-1).view(np.uint8), cores)
+        except Exception:
+            pass
         rec = {"value": round(total_samples / (ms * 1e-3) / 1e6, 2), "unit": "MSamples/s",
                "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "ms_per_step": round(ms, 2),
                "scaling": "strong", "workload": "fixed corpus: %d tracks x %d samples (%.0f s each, %.2f h in all), "
@@ -827,6 +855,10 @@ def run_corpus_leg(lib, api, torch, dist, rank, world, local, host_group, allmax
                          "d2h_gbs": round(stats.d2h_bytes / (my_ms * 1e-3) / 1e9, 1),
                          "host_cores": cores},
                "pcie_probe_gbs": {"h2d": pcie[0], "d2h": pcie[1]} if pcie else None,
+               "host_read_probe_gbs": host_gbs,
+               "host_bytes_per_sample": round((2 * CHANNELS * 2 * total_samples + d2h_b) / float(total_samples), 2),
+               "bound": "N = 1: the GPU's PCIe link (pcie_probe_gbs); more GPUs: host DRAM traffic (MD5 read + DMA read + "
+                        "DMA write per sample against host_read_probe_gbs)",
                "parity": par}
     co.close()
     del h_in, h_out

@@ -16,7 +16,8 @@ n = int(secs * 44100)
 dev = torch.device("cuda", 0)
 lib = api.load_library()
 lib.flake_b200_set_device(0)
-enc = api.Encoder(lib, 2, 44100, 16, n, level)
+ov = {'variable_block_size': 0, 'allow_vbs': 0} if os.environ.get('FLAKE_TEST_NO_VBS') else {}
+enc = api.Encoder(lib, 2, 44100, 16, n, level, **ov)
 enc.init()
 ctx = C.byref(enc.ctx)
 d_pcm = torch.from_numpy(bench.workload_pcm(bench.C2, 0, n).astype(np.int16)).to(dev)

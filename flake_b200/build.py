@@ -59,8 +59,10 @@ def build_product(force: bool = False, variant: str = "", defines=()) -> str:
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     obj_cu = os.path.join(libdir, "engine.o")
-    _run([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] +
-         ["-I", inc, "-c", os.path.join(CSRC, "engine.cu"), "-o", obj_cu])
+    cu_srcs = [f for f in srcs if f.endswith((".cu", ".cuh", ".h"))]
+    if force or defines or _newer(obj_cu, cu_srcs):          # a change of the C host files alone only relinks
+        _run([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] +
+             ["-I", inc, "-c", os.path.join(CSRC, "engine.cu"), "-o", obj_cu])
     objs = [obj_cu]
     for c in HOST_C:
         o = os.path.join(libdir, c.replace(".c", ".o"))

@@ -58,6 +58,7 @@ struct FbEngine {
     cudaEvent_t ev_pass;            /* end of the most recent pass: the scratch buffers are shared between passes */
     cudaStream_t last_stream;       /* stream that pass ran on */
     int have_pass;
+    uint32_t lpc_lat_max;           /* passes with no more subframes run k_lpc_lat (FLAKE_B200_LPC_LAT_MAX overrides) */
     int sync_launches;              /* FLAKE_B200_SYNC_LAUNCHES: name the kernel an asynchronous fault comes from */
     char err[256];
 };
@@ -163,6 +164,7 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     e->out_bytes = e->slot_bytes;
 
     if (cudaEventCreateWithFlags(&e->ev_pass, cudaEventDisableTiming) != cudaSuccess) e->ev_pass = nullptr;
+    { const char *lm = getenv("FLAKE_B200_LPC_LAT_MAX"); e->lpc_lat_max = lm && *lm ? (uint32_t)atoi(lm) : FB_LPC_LAT_MAX_SUBFRAMES; }
     { const char *sl = getenv("FLAKE_B200_SYNC_LAUNCHES"); e->sync_launches = sl && *sl == '1'; }
     ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { set_err(err, errlen, "cudaStreamCreate failed", ce); delete e; return nullptr; }
@@ -243,6 +245,12 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     /* The attribute is per function, per device and per PROCESS, not per engine: every engine sets
      * the same constant (the staging budget), so a later engine with smaller blocks can never
      * lower it under a live engine's launch size. */
+    cudaFuncSetAttribute(k_lpc_lat<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_lpc_lat<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_lpc_lat<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_lpc_lat<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_lpc_lat<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
+    cudaFuncSetAttribute(k_lpc_lat<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
     cudaFuncSetAttribute(k_search<12, FB_SEARCH_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
     cudaFuncSetAttribute(k_search<12, FB_SEARCH_CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
     cudaFuncSetAttribute(k_search<32, FB_SEARCH_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM_BUDGET);
@@ -371,12 +379,27 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
             else if (lk == FB_LPC_LK_S24_STEREO) FB_LPC_GO2(ML_, FB_LPC_LK_S24_STEREO);           \
             else FB_LPC_GO(ML_);                                                                  \
         } while (0)
-        if (cfg.max_order <= 4) FB_LPC_GO(4);
+        /* a handful of blocks (flake_encode_frame: one): the latency form, a warp per subframe */
+        const size_t lat_smem = ((size_t)B + 2u) * sizeof(double);
+        const bool lat = grid_subs <= e->lpc_lat_max && lat_smem <= FB_SMEM_BUDGET;
+#define FB_LPC_LAT(ML_)                                                                           \
+        FB_LAUNCH((k_lpc_lat<ML_>), dim3(grid_subs), dim3(32), lat_smem, st,                      \
+                  cfg, e->d_frames, e->d_nframes, d_pcm, fmt, e->d_smp, e->d_modes, e->d_subs, e->d_coefs, e->d_shifts)
+        if (lat) {
+            if (cfg.max_order <= 4) FB_LPC_LAT(4);
+            else if (cfg.max_order <= 8) FB_LPC_LAT(8);
+            else if (cfg.max_order <= 12) FB_LPC_LAT(12);
+            else if (cfg.max_order <= 16) FB_LPC_LAT(16);
+            else if (cfg.max_order <= 24) FB_LPC_LAT(24);
+            else FB_LPC_LAT(32);
+        }
+        else if (cfg.max_order <= 4) FB_LPC_GO(4);
         else if (cfg.max_order <= 8) FB_LPC_GO3(8);
         else if (cfg.max_order <= 12) FB_LPC_GO3(12);
         else if (cfg.max_order <= 16) FB_LPC_GO(16);
         else if (cfg.max_order <= 24) FB_LPC_GO(24);
         else FB_LPC_GO3(32);
+#undef FB_LPC_LAT
 #undef FB_LPC_GO3
 #undef FB_LPC_GO2
 #undef FB_LPC_GO

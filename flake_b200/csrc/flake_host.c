@@ -59,6 +59,7 @@ typedef struct FbCtx {
     /* batch path */
     FbEngine *engN;             /* host streaming path: chunk_blocks per pass, two lanes */
     FbEngine *engD;             /* device-resident API: dev_chunk_blocks per pass */
+    int profiling;              /* flake_b200_set_profiling: applied to engines created later too */
     FbEngine *last_engine;      /* whichever ran the most recent pass */
     int chunk_blocks, dev_chunk_blocks;
     FbLane lane[2];
@@ -426,14 +427,6 @@ static int lane_launch(FbCtx *c, FbEngine *e, FbLane *l, const void *upload, siz
     return 0;
 }
 
-static int lane_submit(FbCtx *c, FbEngine *e, FbLane *l, const void *pcm, int fmt,
-                       uint64_t nsamples, uint32_t first_number)
-{
-    const void *up; size_t nb; int ufmt;
-    lane_stage(c, l, pcm, fmt, nsamples, &up, &nb, &ufmt);
-    return lane_launch(c, e, l, up, nb, ufmt, first_number);
-}
-
 /* wait for the pass, then pull frames + lengths (exact sizes) on the copy stream */
 static int lane_collect(FbCtx *c, FbLane *l, uint8_t *h_dst, uint64_t dst_cap, int want_bs)
 {
@@ -645,13 +638,29 @@ static int flake_encode_frame_impl(FlakeContext *s, const int *samples, int bloc
     if (c->last_frame) return -1;
     if (!c->params.allow_vbs && block_size != c->params.block_size) c->last_frame = 1;
 
-    if (lane_submit(c, c->eng1, &c->one, samples, FLAKE_B200_PCM_S32, (uint64_t)block_size, c->frame_count))
+    /* One block, one wait: k_pack writes the frame straight into the page-locked frame buffer
+     * (unified addressing: the device reaches it by its host address), so nothing is left to copy
+     * after the pass but the 24-byte summary that travels with it. */
+    FbLane *l = &c->one;
+    const void *up; size_t nb; int ufmt;
+    lane_stage(c, l, samples, FLAKE_B200_PCM_S32, (uint64_t)block_size, &up, &nb, &ufmt);
+    if (fb_cuda_h2d(l->d_in, up, nb, c->st)) return -1;
+    c->stats.h2d_bytes += nb;
+    const uint64_t before = fb_engine_launch_count(c->eng1);
+    if (fb_engine_encode_device(c->eng1, l->d_in, ufmt, (uint64_t)block_size, c->frame_count, c->frame_buffer,
+                                l->d_flen, NULL, l->d_sum, c->st)) {
+        snprintf(c->err, sizeof c->err, "%s", fb_engine_last_error(c->eng1));
         return -1;
+    }
+    c->stats.kernel_launches += fb_engine_launch_count(c->eng1) - before;
+    c->last_engine = c->eng1;
+    if (fb_cuda_d2h(l->h_sum, l->d_sum, sizeof(FbSummary), c->st) || fb_cuda_event_record(l->ev_done, c->st)) return -1;
     /* MD5 of this block while the GPU works (encode.c:1005-1006) */
     FbMd5 md5 = c->md5;
-    fb_md5_update(&md5, c->one.h_pack, c->one.pack_bytes);     /* packed by lane_stage */
-    if (lane_collect(c, &c->one, c->frame_buffer, c->frame_buffer_size, 0)) return -1;
-    const FbSummary *sm = c->one.h_sum;
+    fb_md5_update(&md5, l->h_pack, l->pack_bytes);             /* packed by lane_stage */
+    if (fb_cuda_event_sync(l->ev_done)) { snprintf(c->err, sizeof c->err, "CUDA failure while encoding"); return -1; }
+    const FbSummary *sm = l->h_sum;
+    c->stats.d2h_bytes += sizeof(FbSummary) + sm->total_bytes;
     if (sm->total_bytes == 0 || sm->total_bytes > 0x7fffffffull) return -1;
     account(c, sm, (uint64_t)block_size);
     c->md5 = md5;
@@ -763,6 +772,7 @@ static int ensure_batch_engine(FbCtx *c)
     if (!c->engN) {
         c->engN = fb_engine_create(&c->cfg, c->device, (uint32_t)c->chunk_blocks, c->err, sizeof c->err);
         if (!c->engN) return -3;
+        if (c->profiling) fb_engine_set_timing(c->engN, 1);
     }
     /* lane_alloc starts from a zeroed lane: never called on a live one (lanes_ready guards) */
     if (lane_alloc(&c->lane[0], c->engN, &c->cfg, NULL) || lane_alloc(&c->lane[1], c->engN, &c->cfg, NULL)) {
@@ -967,6 +977,7 @@ static int flake_b200_device_capacity_impl(FlakeContext *s, unsigned long long *
     if (!c->engD) {
         c->engD = fb_engine_create(&c->cfg, c->device, (uint32_t)c->dev_chunk_blocks, c->err, sizeof c->err);
         if (!c->engD) return -3;
+        if (c->profiling) fb_engine_set_timing(c->engD, 1);
     }
     if (max_samples) *max_samples = (unsigned long long)fb_engine_max_blocks(c->engD) * (unsigned long long)c->params.block_size;
     if (out_bytes) *out_bytes = fb_engine_out_capacity(c->engD);
@@ -995,20 +1006,35 @@ int flake_b200_set_profiling(FlakeContext *s, int on)
 {
     if (!s || !s->private_ctx) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    if (flake_b200_device_capacity(s, NULL, NULL, NULL)) return -3;
-    if (on) fb_engine_reset_timing(c->engD);
-    return fb_engine_set_timing(c->engD, on);
+    /* every engine the context owns at this moment: the per-block one, the streaming one, the device one */
+    FbEngine *engs[3] = { c->eng1, c->engN, c->engD };
+    int rc = 0;
+    c->profiling = on ? 1 : 0;
+    for (int i = 0; i < 3; i++) {
+        if (!engs[i]) continue;
+        if (on) fb_engine_reset_timing(engs[i]);
+        if (fb_engine_set_timing(engs[i], on)) rc = -1;
+    }
+    return rc;
 }
 
 int flake_b200_stage_times(FlakeContext *s, double *ms, unsigned long long *launches)
 {
     if (!s || !s->private_ctx) return -1;
     FbCtx *c = (FbCtx *)s->private_ctx;
-    if (!c->engD) return -1;
-    uint64_t l[FB_NUM_STAGES];
-    const int n = fb_engine_collect_timing(c->engD, ms, l);
-    if (launches) for (int i = 0; i < FB_NUM_STAGES; i++) launches[i] = l[i];
-    return n;
+    FbEngine *engs[3] = { c->eng1, c->engN, c->engD };
+    double tot[FB_NUM_STAGES] = { 0 };
+    uint64_t cnt[FB_NUM_STAGES] = { 0 };
+    for (int k = 0; k < 3; k++) {
+        double m[FB_NUM_STAGES]; uint64_t l[FB_NUM_STAGES];
+        if (!engs[k] || fb_engine_collect_timing(engs[k], m, l) < 0) continue;
+        for (int i = 0; i < FB_NUM_STAGES; i++) { tot[i] += m[i]; cnt[i] += l[i]; }
+    }
+    for (int i = 0; i < FB_NUM_STAGES; i++) {
+        if (ms) ms[i] = tot[i];
+        if (launches) launches[i] = cnt[i];
+    }
+    return FB_NUM_STAGES;
 }
 
 int flake_b200_set_streaminfo_sizes(FlakeContext *s, int on)

@@ -135,6 +135,96 @@ __device__ __forceinline__ void fb_store_row(int32_t *co, int32_t *so, int rowi,
 }
 
 /*
+ * From the autocorrelation to the quantised coefficient rows: Levinson-Durbin (lpc.c:77-117) or the
+ * Schur order estimate (lpc.c:125-156), the 15-bit quantiser (lpc.c:167-219).  Every calling lane
+ * computes the same recursion; `writer` stores the rows.  only_row >= 0 (latency kernel): this
+ * lane quantises and stores row only_row alone, so that the rows of one subframe are quantised
+ * side by side instead of one after the other.
+ */
+template <int ML>
+__device__ __forceinline__ void fb_lpc_rows(const FbConfig &cfg, const double (&autoc)[ML + 1], int lag, uint32_t sf,
+                                            bool writer, FbSub *sb, int32_t *coefs_out, int32_t *shift_out,
+                                            int only_row = -1)
+{
+    int32_t *co = coefs_out + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
+    int32_t *so = shift_out + (size_t)sf * FB_MAX_ORDER;
+    const int om = cfg.order_method;
+    double a[ML];
+#pragma unroll
+    for (int i = 0; i < ML; i++) a[i] = 0.0;
+
+    if (om == 1) {
+        /* Schur recursion and order estimate, lpc.c:125-154 */
+        double g0[ML], g1[ML], refl[ML];
+#pragma unroll
+        for (int i = 0; i < ML; i++) { g0[i] = g1[i] = autoc[i + 1]; refl[i] = 0.0; }
+        double e = autoc[0];
+        refl[0] = __ddiv_rn(-g1[0], e);
+        e = __dadd_rn(e, __dmul_rn(g1[0], refl[0]));
+#pragma unroll
+        for (int i = 1; i < ML; i++) {
+            if (i < lag) {
+#pragma unroll
+                for (int j = 0; j < ML - i; j++) {
+                    if (j < lag - i) {
+                        const double g1n = g1[j + 1];
+                        g1[j] = __dadd_rn(g1n, __dmul_rn(refl[i - 1], g0[j]));
+                        g0[j] = __dadd_rn(__dmul_rn(g1n, refl[i - 1]), g0[j]);
+                    }
+                }
+                refl[i] = __ddiv_rn(-g1[0], e);
+                e = __dadd_rn(e, __dmul_rn(g1[0], refl[i]));
+            }
+        }
+        int est = 1;
+#pragma unroll
+        for (int i = 0; i < ML; i++)
+            if (i < lag && fabs(refl[i]) > 0.10) est = i + 1;           /* highest such i */
+        /* Levinson from the reflection coefficients up to the estimate, lpc.c:156 */
+#pragma unroll
+        for (int i = 0; i < ML; i++)
+            if (i < est) fb_levinson_update<ML>(a, i, refl[i]);
+        double rowv[ML];
+        int32_t q[ML], sh;
+#pragma unroll
+        for (int j = 0; j < ML; j++) rowv[j] = -a[j];
+        fb_quantize<ML>(rowv, est, q, sh);
+        if (writer) {
+#pragma unroll
+            for (int j = 0; j < ML; j++)
+                if (j < est) co[(est - 1) * FB_MAX_ORDER + j] = q[j];
+            so[est - 1] = sh;
+            sb->est_order = est;
+        }
+        return;
+    }
+
+    /* Levinson-Durbin, lpc.c:77-117; rows are quantised as they appear */
+    double err = autoc[0];
+#pragma unroll
+    for (int i = 0; i < ML; i++) {
+        if (i < lag) {
+            double r = -autoc[i + 1];
+#pragma unroll
+            for (int j = 0; j < i; j++)
+                r = __dsub_rn(r, __dmul_rn(a[j], autoc[i - j]));
+            r = __ddiv_rn(r, err);
+            err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
+            fb_levinson_update<ML>(a, i, r);
+            if ((om >= 2 || i == lag - 1) && (only_row < 0 || only_row == i)) {
+                double rowv[ML];
+                int32_t q[ML], sh;
+#pragma unroll
+                for (int j = 0; j < ML; j++) rowv[j] = j <= i ? -a[j] : 0.0;
+                fb_quantize<ML>(rowv, i + 1, q, sh);
+                if (writer) fb_store_row<ML>(co, so, i, q, sh);
+            }
+        }
+    }
+    if (writer && only_row < 0) sb->est_order = lag;
+}
+
+/*
  * coefs_out: [subframe][32][32] int32 (row = order-1, entries 0..order-1 written),
  * shift_out: [subframe][32].  Grid: ceil(subframes / FB_LPC_SUBS_PER_CTA) CTAs.
  */
@@ -340,83 +430,124 @@ k_lpc(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const void *
         autoc[i] = __dadd_rn(acc[i], __shfl_xor_sync(FB_FULL_MASK, acc[i], 1));
 
     if (n == 0) return;
-    const bool writer = ca == 0;
-    int32_t *co = coefs_out + (size_t)sf * FB_MAX_ORDER * FB_MAX_ORDER;
-    int32_t *so = shift_out + (size_t)sf * FB_MAX_ORDER;
+    fb_lpc_rows<ML>(cfg, autoc, lag, sf, ca == 0, sb, coefs_out, shift_out);
+}
+
+/*
+ * Latency form of the same analysis, for passes of a few blocks (flake_encode_frame: one block
+ * per synchronous call).  k_lpc is built for throughput -- a lane pair walks a whole subframe,
+ * 152 us for one 4096-sample block when there are no other warps to hide behind.  Here a WARP
+ * owns a subframe and a LANE owns one accumulator chain of one lag (lpc.c:57-68: `temp` over
+ * the head and the odd tail terms, `temp2` over the even ones; lags beyond 15 take a second and
+ * third chain per lane, NS), so the 2 (lag + 1) strictly ordered sums advance side by side and the
+ * time is one chain's: n / 2 dependent additions.  The windowed signal is computed once, by all
+ * lanes, into shared memory; each step reads data1[j] (broadcast) and data1[j - i].  Two 64-bit
+ * shared loads per multiply-add make this form LSU-bound in bulk (3.3 ms per C2 stream in round
+ * 1), which is why it is only launched for small passes.  Same operations in the same order as
+ * k_lpc: byte-identical rows.  Dynamic shared memory: (n + 2) doubles.
+ */
+#define FB_LPC_LAT_MAX_SUBFRAMES 2048        /* engine.cu: passes with no more subframes take this kernel (crossover ~3500) */
+
+template <int ML>
+__global__ void __launch_bounds__(32)
+k_lpc_lat(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const void *pcm, int fmt,
+          const int32_t *planes, const uint8_t *ch_modes, FbSub *subs, int32_t *coefs_out, int32_t *shift_out)
+{
+    constexpr int NS = (2 * (ML + 1) + 31) / 32;            /* chains per lane: 2 (ML + 1) accumulators over 32 lanes */
+    FB_DYN_SMEM(dyn);
+    double *d = reinterpret_cast<double *>(dyn);
+    const int lane = threadIdx.x;
+    const int C = cfg.channels, lag = cfg.max_order;
+    const uint32_t sf = blockIdx.x;
+    if (sf >= *nframes * (uint32_t)C) return;
+    const uint32_t f = sf / (uint32_t)C;
+    const int c = (int)(sf % (uint32_t)C);
+    const FbFrame fr = frames[f];
+    FbSub *sb = &subs[sf];
+    /* same gate as optimize.c:143-193: only the LPC branch needs coefficients */
+    if (sb->is_const || fr.n < 5u || cfg.prediction_type != 2 || (int)fr.n <= lag) return;
+    const int n = (int)fr.n;
+    const int mode = ch_modes[f], wasted = sb->wasted;
+    const size_t ebase = (size_t)fr.start * C;
+
+    /* data1[] of lpc.c:46-56; the centre of an odd block is zero (see fb_windowed) */
+    const double cc = __dsub_rn(__ddiv_rn(2.0, __dsub_rn((double)n, 1.0)), 1.0);
+    /* eight positions per lane at a time: their loads are in flight together (one at a time, the
+     * load latency of 128 dependent round trips was most of the kernel) */
+    for (int p0 = lane; p0 < n; p0 += 32 * 8) {
+        int32_t xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int p = p0 + 32 * u;
+            xv[u] = 0;
+            if (p < n && !((n & 1) && p == (n >> 1)))
+                xv[u] = fb_uses_planes(C) ? planes[ebase + (size_t)c * (size_t)n + (size_t)p]
+                                          : fb_pcm_sample(pcm, fmt, ebase, C, c, mode, wasted, p);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int p = p0 + 32 * u;
+            if (p < n) d[p] = fb_windowed(xv[u], p, n, cc);
+        }
+    }
+    if (lane < 2) d[n + lane] = 0.0;                      /* data1[len] = 0 */
+    __syncwarp();
+
+    /* chain q = 2 i + ca of lane (q % 32), slot (q / 32) */
+    double acc[NS];
+    int lagi[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const int q = lane + 32 * s;
+        const int i = q >> 1, ca = q & 1;
+        lagi[s] = i <= lag ? i : -1;
+        double t = 1.0;
+        if (i <= lag && ca == 0)
+            for (int j = 0; j <= lag - i; j++) t = __dadd_rn(t, __dmul_rn(d[j + i], d[j]));
+        acc[s] = t;
+    }
+    const int ca = lane & 1;                               /* the same for every slot: 32 is even */
+    /* temp: j = lag+1, lag+3, ...; temp2: the positions after them.  Eight steps at a time: the
+     * loads and products of a batch are independent, only the additions form the chain */
+    int j = lag + 1 + ca;
+    const int jend = n - 1 + ca;                           /* last position, inclusive */
+    for (; j + 14 <= jend; j += 16) {
+        double pr[NS][8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const double dj = d[j + 2 * u];
+#pragma unroll
+            for (int s = 0; s < NS; s++)
+                pr[s][u] = lagi[s] >= 0 ? __dmul_rn(dj, d[j + 2 * u - lagi[s]]) : 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (lagi[s] >= 0) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[s] = __dadd_rn(acc[s], pr[s][u]);
+            }
+    }
+    for (; j <= jend; j += 2) {
+        const double dj = d[j];
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (lagi[s] >= 0) acc[s] = __dadd_rn(acc[s], __dmul_rn(dj, d[j - lagi[s]]));
+    }
+
+    /* autoc[i] = temp + temp2 (lpc.c:67), gathered to every lane */
+    double autoc[ML + 1];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const double pair = __dadd_rn(__shfl_sync(FB_FULL_MASK, acc[s], lane & ~1), __shfl_sync(FB_FULL_MASK, acc[s], lane | 1));
+#pragma unroll
+        for (int i = 16 * s; i < 16 * s + 16; i++)
+            if (i <= ML) autoc[i] = __shfl_sync(FB_FULL_MASK, pair, 2 * (i - 16 * s));
+    }
+    /* row `lane` is quantised by lane `lane`; the order estimate needs one row only */
     const int om = cfg.order_method;
-    double a[ML];
-#pragma unroll
-    for (int i = 0; i < ML; i++) a[i] = 0.0;
-
-    if (om == 1) {
-        /* Schur recursion and order estimate, lpc.c:125-154 */
-        double g0[ML], g1[ML], refl[ML];
-#pragma unroll
-        for (int i = 0; i < ML; i++) { g0[i] = g1[i] = autoc[i + 1]; refl[i] = 0.0; }
-        double e = autoc[0];
-        refl[0] = __ddiv_rn(-g1[0], e);
-        e = __dadd_rn(e, __dmul_rn(g1[0], refl[0]));
-#pragma unroll
-        for (int i = 1; i < ML; i++) {
-            if (i < lag) {
-#pragma unroll
-                for (int j = 0; j < ML - i; j++) {
-                    if (j < lag - i) {
-                        const double g1n = g1[j + 1];
-                        g1[j] = __dadd_rn(g1n, __dmul_rn(refl[i - 1], g0[j]));
-                        g0[j] = __dadd_rn(__dmul_rn(g1n, refl[i - 1]), g0[j]);
-                    }
-                }
-                refl[i] = __ddiv_rn(-g1[0], e);
-                e = __dadd_rn(e, __dmul_rn(g1[0], refl[i]));
-            }
-        }
-        int est = 1;
-#pragma unroll
-        for (int i = 0; i < ML; i++)
-            if (i < lag && fabs(refl[i]) > 0.10) est = i + 1;           /* highest such i */
-        /* Levinson from the reflection coefficients up to the estimate, lpc.c:156 */
-#pragma unroll
-        for (int i = 0; i < ML; i++)
-            if (i < est) fb_levinson_update<ML>(a, i, refl[i]);
-        double rowv[ML];
-        int32_t q[ML], sh;
-#pragma unroll
-        for (int j = 0; j < ML; j++) rowv[j] = -a[j];
-        fb_quantize<ML>(rowv, est, q, sh);
-        if (writer) {
-#pragma unroll
-            for (int j = 0; j < ML; j++)
-                if (j < est) co[(est - 1) * FB_MAX_ORDER + j] = q[j];
-            so[est - 1] = sh;
-            sb->est_order = est;
-        }
-        return;
-    }
-
-    /* Levinson-Durbin, lpc.c:77-117; rows are quantised as they appear */
-    double err = autoc[0];
-#pragma unroll
-    for (int i = 0; i < ML; i++) {
-        if (i < lag) {
-            double r = -autoc[i + 1];
-#pragma unroll
-            for (int j = 0; j < i; j++)
-                r = __dsub_rn(r, __dmul_rn(a[j], autoc[i - j]));
-            r = __ddiv_rn(r, err);
-            err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(r, r)));
-            fb_levinson_update<ML>(a, i, r);
-            if (om >= 2 || i == lag - 1) {
-                double rowv[ML];
-                int32_t q[ML], sh;
-#pragma unroll
-                for (int j = 0; j < ML; j++) rowv[j] = j <= i ? -a[j] : 0.0;
-                fb_quantize<ML>(rowv, i + 1, q, sh);
-                if (writer) fb_store_row<ML>(co, so, i, q, sh);
-            }
-        }
-    }
-    if (writer) sb->est_order = lag;
+    fb_lpc_rows<ML>(cfg, autoc, lag, sf, om == 1 ? lane == 0 : lane < lag, sb, coefs_out, shift_out,
+                    om == 1 ? -1 : (om >= 2 ? lane : (lane == 0 ? lag - 1 : 99)));
+    if (om != 1 && lane == 0) sb->est_order = lag;
 }
 
 #endif

@@ -125,8 +125,8 @@ FLAKE_API int flake_b200_last_subframes(FlakeContext *s, void *subs, unsigned in
 FLAKE_API unsigned int flake_b200_subframe_record_size(void);
 
 /*
- * Per-stage device timing of the DEVICE-RESIDENT engine (flake_b200_encode_device; the host-buffer
- * calls run on engines of their own and are not instrumented), measured with CUDA events
+ * Per-stage device timing of every pass of the context (flake_encode_frame, the streaming calls
+ * and flake_b200_encode_device alike; the totals are sums over them), measured with CUDA events
  * recorded between the kernels on the launching stream.  Five stages:
  * 0 frame table (+VBS split), 1 prepare, 2 LPC analysis, 3 order/Rice search,
  * 4 pack (bits, CRCs, frame offsets, frames written back to back).

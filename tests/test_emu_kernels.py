@@ -38,8 +38,11 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("lpc", ["throughput", "latency"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_emulated_kernels_match_oracle(case, emu_lib, oracle):
+def test_emulated_kernels_match_oracle(case, lpc, emu_lib, oracle, monkeypatch):
+    # small passes would all take the latency form of the LPC analysis (k_lpc_lat): run both kernels
+    monkeypatch.setenv("FLAKE_B200_LPC_LAT_MAX", "0" if lpc == "throughput" else "100000")
     name, n, ch, bps, rate, kind, level, ov = case
     pcm = synth.synth_pcm(n, ch, bps, rate, seed=len(name) * 7 + level, kind=kind)
     got = api.encode_batch(emu_lib, pcm, rate, bps, level, chunk_blocks=2, **ov)

@@ -61,10 +61,16 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_batch_matches_oracle(case, gpu_lib, oracle):
+def test_batch_matches_oracle(case, gpu_lib, oracle, monkeypatch):
     name, n, ch, bps, rate, kind, level, ov = case
     pcm = synth.synth_pcm(n, ch, bps, rate, seed=zlib.crc32(name.encode()) % 1000, kind=kind)
+    # passes this small take the latency form of the LPC analysis (k_lpc_lat); the throughput form
+    # (k_lpc) must produce the same bytes
+    monkeypatch.setenv("FLAKE_B200_LPC_LAT_MAX", "0")
+    bulk = api.encode_batch(gpu_lib, pcm, rate, bps, level, chunk_blocks=4, **ov)
+    monkeypatch.delenv("FLAKE_B200_LPC_LAT_MAX")
     got = api.encode_batch(gpu_lib, pcm, rate, bps, level, chunk_blocks=4, **ov)
+    assert got.payload == bulk.payload and got.streaminfo == bulk.streaminfo
     want, flen, fbs, mx = oracle.encode_stream(pcm, rate, bps, level, **ov)
     assert list(map(len, got.frames)) == list(flen)
     assert list(got.frame_bs) == list(fbs)

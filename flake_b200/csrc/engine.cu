@@ -237,7 +237,8 @@ extern "C" FbEngine *fb_engine_create(const FbConfig *cfg, int device, uint32_t 
     }
     if (cfg->prediction_type == 2 && cfg->order_method == 6) {
         const int group = cfg->max_order > 12 ? FB_GROUP_OF(32) : FB_GROUP_OF(12);
-        const std::vector<FbPlanNode> plan = fb_build_log_plan(cfg->min_order, cfg->max_order, group);
+        std::vector<FbPlanNode> plan = fb_build_log_plan(cfg->min_order, cfg->max_order, group);
+        if (plan.size() < FB_PLAN_SMEM_NODES) plan.resize(FB_PLAN_SMEM_NODES);      /* k_search stages that many */
         cudaError_t ce_ = cudaMalloc((void **)&e->d_plan, plan.size() * sizeof(FbPlanNode));
         if (ce_ == cudaSuccess) ce_ = cudaMemcpy(e->d_plan, plan.data(), plan.size() * sizeof(FbPlanNode), cudaMemcpyHostToDevice);
         if (ce_ != cudaSuccess) { set_err(err, errlen, "search plan upload failed", ce_); fb_engine_destroy(e); return nullptr; }

@@ -40,6 +40,7 @@
  * independent candidates and the fourth run-sum array only costs shared memory (3.174 vs 3.187 ms);
  * the order-32 kernel takes four (exhaustive search of C3: 6.02 -> 5.56 ms). */
 #define FB_GROUP_MAX 4
+#define FB_PLAN_SMEM_NODES 12    /* nodes of the log-search plan staged in shared memory (all of them up to order 12) */
 #define FB_GROUP_OF(MAXP) ((MAXP) > 12 ? 4 : 3)
 
 /* dev builds (-DFB_SEARCH_PROF): cycles per phase as seen by thread 0, summed over all CTAs */
@@ -83,6 +84,7 @@ struct FbSearchShared {
     int32_t  porder[FB_GROUP_MAX], method[FB_GROUP_MAX];
     int32_t  best_porder, best_method;
     uint32_t best_bits;
+    FbPlanNode plan[FB_PLAN_SMEM_NODES];
 };
 
 /*
@@ -257,6 +259,100 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
         return;
     }
     fb_finish_body<MAXP, uint32_t>(S, slot, F, per, n, is_lpc, order, obits, pmin, pmax);
+}
+
+/*
+ * The finish for the common shape: 32-bit run sums (F32, one word per run, written by the 32-bit
+ * run bodies), n a power of two from 512 to FB_FAST_MAX_N, every partition sum below 2^31
+ * (S.sum32_of).  Levels 5 and up: a partition is 1, 2, 4 or 8 consecutive run sums -- one or two
+ * vector loads -- partitions lane-strided; level 5 leaves every lane the sum of its own
+ * partition.  Levels 4 .. 0: five xor shuffles give every lane the sum of the partition it
+ * belongs to, and EVERY lane costs one partition (rice.c:30-74): lane l takes level 5 - c,
+ * c = 1 + ctz(l), partition l >> c -- 16 + 8 + 4 + 2 + 1 lanes, one Rice computation for five
+ * levels; the level totals are xor steps that keep the lowest set bit of the lane index in
+ * place.  A parameter above 14 (RICE2) is counted in bits 20 and up of the same word.  The best
+ * level is the smallest total, the finer one on a tie (rice.c:128-135): one minimum over
+ * (bits, 31 - level, method).  Same posts as fb_finish_body.
+ */
+#define FB_FAST_MAX_N 4096
+
+__device__ __forceinline__ uint32_t fb_level_key(uint32_t x, int L)
+{
+    return (((x & 0xfffffu) + (4u << L)) << 6) | ((uint32_t)(31 - L) << 1) | ((x >> 20) ? 1u : 0u);
+}
+
+template <int MAXP>
+__device__ __noinline__ void fb_finish_fast(FbSearchShared<MAXP> &S, int slot, const uint32_t *F32, int n, int is_lpc,
+                                            int order, int obits, int pmin, int pmax)
+{
+    const int lane = threadIdx.x & 31;
+    uint8_t *kbuf = S.kbuf[slot];
+    const int ltop = 27 - __clz(n);                               /* the level whose partitions are single runs */
+    uint32_t key = 0xffffffffu, a3 = 0;
+    const int lfirst = pmax < 5 ? 5 : (pmax < ltop ? pmax : ltop);
+#pragma unroll 1
+    for (int L = lfirst; L >= 5; L--) {
+        const int e = ltop - L;
+        uint32_t x = 0;
+#pragma unroll 1
+        for (int j = lane; j < (1 << L); j += 32) {
+            const uint32_t *src = F32 + (j << e);
+            uint32_t sum;
+            if (e == 3) {
+                const uint4 p = *reinterpret_cast<const uint4 *>(src), q = *reinterpret_cast<const uint4 *>(src + 4);
+                sum = ((p.x + p.y) + (p.z + p.w)) + ((q.x + q.y) + (q.z + q.w));
+            } else if (e == 2) {
+                const uint4 p = *reinterpret_cast<const uint4 *>(src);
+                sum = (p.x + p.y) + (p.z + p.w);
+            } else if (e == 1) {
+                const uint2 p = *reinterpret_cast<const uint2 *>(src);
+                sum = p.x + p.y;
+            } else {
+                sum = src[0];
+            }
+            const int cnt = (16 << e) - (j == 0 ? order : 0);     /* runs of 16 samples (FB_RUN) */
+            const int k = fb_rice_k_t(sum, cnt);
+            kbuf[(1 << L) - 1 + j] = (uint8_t)k;
+            x += fb_rice_count_t(sum, cnt, k) + (k > 14 ? (1u << 20) : 0u);
+            a3 = sum;
+        }
+        x = __reduce_add_sync(FB_FULL_MASK, x);
+        if (L <= pmax && L >= pmin) key = min(key, fb_level_key(x, L));
+    }
+    /* across the lanes: levels 4 .. 0 */
+    if (pmin < 5) {
+        const uint32_t c1 = a3 + __shfl_xor_sync(FB_FULL_MASK, a3, 1);
+        const uint32_t c2 = c1 + __shfl_xor_sync(FB_FULL_MASK, c1, 2);
+        const uint32_t c3 = c2 + __shfl_xor_sync(FB_FULL_MASK, c2, 4);
+        const uint32_t c4 = c3 + __shfl_xor_sync(FB_FULL_MASK, c3, 8);
+        const uint32_t c5 = c4 + __shfl_xor_sync(FB_FULL_MASK, c4, 16);
+        const int c = lane ? __ffs(lane) : 6;
+        const int L = 5 - c;
+        const uint32_t sum = c == 1 ? c1 : (c == 2 ? c2 : (c == 3 ? c3 : (c == 4 ? c4 : c5)));
+        const int j = lane >> c;
+        const int cnt = (n >> (L < 0 ? 0 : L)) - (j == 0 ? order : 0);
+        const int k = fb_rice_k_t(sum, cnt);
+        const bool use = lane != 0 && L <= pmax && L >= pmin;
+        uint32_t x = use ? fb_rice_count_t(sum, cnt, k) + (k > 14 ? (1u << 20) : 0u) : 0u;
+        if (use) kbuf[(1 << L) - 1 + j] = (uint8_t)k;
+#pragma unroll
+        for (int o = 1; o < 5; o++) {
+            const uint32_t t = __shfl_xor_sync(FB_FULL_MASK, x, 1 << o);
+            if (o >= c) x += t;
+        }
+        if (use) key = min(key, fb_level_key(x, L));
+    }
+    key = __reduce_min_sync(FB_FULL_MASK, key);
+    if (lane == 0) {
+        const bool none = key == 0xffffffffu;                     /* no level allowed: fb_finish_body's untouched best */
+        const uint32_t bmethod = none ? 0u : key & 1u;
+        uint32_t total = (uint32_t)(order * obits + 2);
+        if (is_lpc) total += 4u + 5u + (uint32_t)order * 15u;
+        total += (none ? 0xffffffffu : key >> 6) + bmethod + 4u;
+        S.result[slot] = total;
+        S.porder[slot] = none ? pmin : 31 - (int)((key >> 1) & 31u);
+        S.method[slot] = (int)bmethod;
+    }
 }
 
 /* group member `slot` is the best candidate so far: warp 0 keeps its parameters */
@@ -633,7 +729,7 @@ __device__ __forceinline__ FbOrders fb_order_put(FbOrders o, int m, int order) {
  * member's run-sum buffer.  The kernel is bound by instruction fetch and per-run latency, not by
  * the multiplies: the zero taps are free, the shared window and the single body are not.
  */
-template <int MAXP, int P, bool WIDE>
+template <int MAXP, int P, bool WIDE, bool RS32>
 __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int count,
                                             FbOrders ord, unsigned long long *runsum0, int rstride)
 {
@@ -713,31 +809,39 @@ __device__ __noinline__ void fb_tiles_group(FbSearchShared<MAXP> &S, const int32
                         a32 = __sad(4 * rk + 1, 0, a32);
                     }
                 }
-                runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)((a32 - FB_RUN) >> 1);
+                /* RS32: one 32-bit word per run, the layout fb_finish_fast reads with 128-bit loads */
+                if constexpr (RS32 && !WIDE) reinterpret_cast<uint32_t *>(runsum0)[m * 2 * rstride + i0 / FB_RUN] = (a32 - FB_RUN) >> 1;
+                else runsum0[m * rstride + i0 / FB_RUN] = WIDE ? acc : (unsigned long long)((a32 - FB_RUN) >> 1);
             }
         }
     }
 }
 
+/* returns true when the run sums were left as 32-bit words (fb_finish_fast finishes) */
 template <int MAXP>
-__device__ __noinline__ void fb_residual_group(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int count,
-                                               FbOrders ord, uint32_t maxabs, unsigned long long *runsum0, int rstride)
+__device__ __forceinline__ bool fb_residual_group(FbSearchShared<MAXP> &S, const int32_t *xs, int n, int is_lpc, int count,
+                                                  FbOrders ord, bool fastable, unsigned long long *runsum0, int rstride)
 {
-    bool narrow = true;
+    bool narrow = true, sum32 = true;
     int omax = 0;
     for (int m = 0; m < count; m++) {
         const int order = fb_order_of(ord, m);
         narrow = narrow && S.narrow_of[is_lpc ? order - 1 : order];
+        sum32 = sum32 && S.sum32_of[is_lpc ? order - 1 : order];
         omax = max(omax, order);
     }
     /* one body per kernel for orders up to 12; the order-32 kernel keeps a body per 4 taps */
     const int P = (MAXP <= 12) ? 12 : ((omax + 3) & ~3);
 #define FB_CASE(PP)                                                                                         \
     case PP:                                                                                                \
-        if (narrow) fb_tiles_group<MAXP, PP, false>(S, xs, n, is_lpc, count, ord, runsum0, rstride);        \
-        else        fb_tiles_group<MAXP, PP, true>(S, xs, n, is_lpc, count, ord, runsum0, rstride);         \
+        if (narrow) fb_tiles_group<MAXP, PP, false, false>(S, xs, n, is_lpc, count, ord, runsum0, rstride); \
+        else        fb_tiles_group<MAXP, PP, true, false>(S, xs, n, is_lpc, count, ord, runsum0, rstride);  \
         break;
     if constexpr (MAXP <= 12) {
+        if (narrow && sum32 && fastable) {
+            fb_tiles_group<MAXP, 12, false, true>(S, xs, n, is_lpc, count, ord, runsum0, rstride);
+            return true;
+        }
         switch (P) { default: FB_CASE(12) }
     } else {
         switch (P) {
@@ -747,6 +851,7 @@ __device__ __noinline__ void fb_residual_group(FbSearchShared<MAXP> &S, const in
         }
     }
 #undef FB_CASE
+    return false;
 }
 
 /* what a group evaluation needs to know about the subframe */
@@ -756,6 +861,7 @@ struct FbSearchCtx {
     int n, obits, pmin, pmax, is_lpc;
     uint32_t maxabs;
     bool fast, tileable;        /* tileable: every partition size is a whole number of runs */
+    bool fastable;              /* fast, tileable, n a power of two from 512 to FB_FAST_MAX_N: fb_finish_fast applies */
 };
 
 /*
@@ -772,12 +878,13 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
     if (X.fast && X.tileable) {
         unsigned long long *runsum0 = reinterpret_cast<unsigned long long *>(const_cast<int32_t *>(X.xs) + fb_skew_words(X.n));
         const int rstride = fb_runsum_words(X.n) / 2;
+        bool rs32 = false;
         if (res_out) {
             const int order = fb_order_of(ord, 0), row = X.is_lpc ? order - 1 : order;
             const int pmax = S.pmax_of[order];
             fb_residual_pass<MAXP, FB_SUMS | FB_STORE>(S, X.xs, X.n, order, row, X.n >> pmax, X.maxabs, res_out, runsum0);
         } else {
-            fb_residual_group<MAXP>(S, X.xs, X.n, X.is_lpc, count, ord, X.maxabs, runsum0, rstride);
+            rs32 = fb_residual_group<MAXP>(S, X.xs, X.n, X.is_lpc, count, ord, X.fastable, runsum0, rstride);
         }
         FB_PROF(1);
         __syncthreads();
@@ -785,7 +892,8 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
         for (int s = tid >> 5; s < count; s += (int)(blockDim.x >> 5)) {
             const int order = fb_order_of(ord, s);
             const int pmin = S.pmin_of[order], pmax = S.pmax_of[order];
-            fb_finish_warp<MAXP>(S, s, runsum0 + s * rstride, (X.n >> pmax) / FB_RUN, X.n, X.is_lpc, order, X.obits, pmin, pmax);
+            if (rs32) fb_finish_fast<MAXP>(S, s, reinterpret_cast<const uint32_t *>(runsum0) + s * 2 * rstride, X.n, X.is_lpc, order, X.obits, pmin, pmax);
+            else fb_finish_warp<MAXP>(S, s, runsum0 + s * rstride, (X.n >> pmax) / FB_RUN, X.n, X.is_lpc, order, X.obits, pmin, pmax);
         }
         FB_PROF(3);
         __syncthreads();
@@ -914,6 +1022,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
         /* the finest partition any candidate can use: larger ones are multiples of it */
         const int pfin = fb_limit_porder(cfg.max_porder, n, 0);
         X.tileable = ((n >> pfin) % FB_RUN) == 0;
+        X.fastable = FB_RUN == 16 && fast && X.tileable && (n & (n - 1)) == 0 && n >= 512 && n <= FB_FAST_MAX_N;
     }
 
     /* candidate rows: binomial coefficients (optimize.c:44-66 is LPC with shift 0) or the
@@ -941,6 +1050,8 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
         }
         for (int rowi = tid; rowi < MAXP; rowi += T) S.shift[rowi] = rowi < max_order ? so[rowi] : 0;
     }
+    if (cfg.order_method == 6 && tid < (int)(FB_PLAN_SMEM_NODES * sizeof(FbPlanNode) / 4))   /* engine.cu pads the plan */
+        reinterpret_cast<uint32_t *>(S.plan)[tid] = reinterpret_cast<const uint32_t *>(plan)[tid];
     for (int o = tid; o <= MAXP; o += T) {
         S.pmin_of[o] = (uint8_t)fb_limit_porder(cfg.min_porder, n, o);
         S.pmax_of[o] = (uint8_t)fb_limit_porder(cfg.max_porder, n, o);
@@ -1115,7 +1226,7 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
         opt_order = (int)plan[0].start_order;
         int step = 16;
         while (node != FB_PLAN_END) {
-            const FbPlanNode nd = plan[node];
+            const FbPlanNode nd = node < FB_PLAN_SMEM_NODES ? S.plan[node] : plan[node];
             const int cnt = (int)nd.cnt, nsteps = (int)nd.nsteps;
             ord = nd.ord;
             FB_PROF(5);

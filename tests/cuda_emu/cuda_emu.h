@@ -222,6 +222,16 @@ inline int __reduce_max_sync(unsigned mask, int v)
     cuemu::warp_barrier(mask);
     return r;
 }
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v)
+{
+    cuemu::WarpState &w = cuemu::my_warp();
+    w.slot[cuemu::lane_id()] = v;
+    cuemu::warp_barrier(mask);
+    unsigned r = 0xffffffffu;
+    for (int l = 0; l < 32; l++) if ((mask >> l) & 1u) r = std::min(r, (unsigned)w.slot[l]);
+    cuemu::warp_barrier(mask);
+    return r;
+}
 inline int __reduce_min_sync(unsigned mask, int v)
 {
     cuemu::WarpState &w = cuemu::my_warp();

@@ -35,6 +35,13 @@ CASES = [
     ("noise_s24_l8", 1024 * 2, 2, 24, 96000, "noise", 8, {"block_size": 1024}),
     ("wasted_l5", 1024, 2, 16, 44100, "wasted", 5, {"block_size": 1024}),
     ("silence_l8", 1024, 2, 16, 44100, "silence", 8, {"block_size": 1024}),
+    # the fused finish of k_search (16-bit, power-of-two blocks of 512..4096): partition order up to 8 (the level
+    # of single runs), one span only, Rice parameters above 14 (RICE2) and the variable-block-size splits
+    ("fused_l9_vbs", 4096 + 100, 2, 16, 44100, "mix", 9, {}),
+    ("fused_l10_bs512", 512 * 3, 2, 16, 44100, "mix", 10, {"block_size": 512, "variable_block_size": 0}),
+    ("fused_l8_bs2048", 2048 * 2 + 17, 2, 16, 44100, "mix", 8, {"block_size": 2048}),
+    ("fused_noise_l8", 4096, 2, 16, 44100, "noise", 8, {}),
+    ("fused_noise_l10", 2048, 1, 16, 44100, "noise", 10, {"block_size": 2048, "variable_block_size": 0}),
 ]
 
 

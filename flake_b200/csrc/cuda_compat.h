@@ -39,14 +39,18 @@ __device__ __forceinline__ void fb_cp_async_wait_all(void)
 /* ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ----------------------
  * cp.async.bulk (SASS: UBLKCP) moves a contiguous byte range with ONE instruction issued by
  * one thread; the mbarrier counts the bytes that land (complete_tx).  Source, destination and
- * size are multiples of 16 bytes.  The emulation copies at issue time and never waits. */
+ * size are multiples of 16 bytes.  The emulation copies at issue time. */
 #ifdef FLAKE_B200_CUDA_EMU
+/* the barrier word counts completed phases: a phase = one expect_tx (+ its copy, done on the spot by
+ * the issuing fiber, which does not yield in between); a waiter yields until the phase of the parity
+ * it names is over, like mbarrier.try_wait.parity -- a fiber that runs ahead of the issuing one must
+ * not read the stage before its refill */
 typedef unsigned long long fb_mbar_t;
 static inline void fb_mbar_init(fb_mbar_t *bar, unsigned) { *bar = 0; }
 static inline void fb_mbar_init_fence(void) {}
-static inline void fb_mbar_expect_tx(fb_mbar_t *, unsigned) {}
+static inline void fb_mbar_expect_tx(fb_mbar_t *bar, unsigned) { *(volatile fb_mbar_t *)bar += 1; }
 static inline void fb_bulk_g2s(void *dst_shared, const void *src_global, unsigned bytes, fb_mbar_t *) { memcpy(dst_shared, src_global, bytes); }
-static inline void fb_mbar_wait(fb_mbar_t *, unsigned) {}
+static inline void fb_mbar_wait(fb_mbar_t *bar, unsigned parity) { while ((*(volatile fb_mbar_t *)bar & 1u) == parity) cuemu::yield(); }
 #else
 typedef unsigned long long fb_mbar_t;
 __device__ __forceinline__ void fb_mbar_init(fb_mbar_t *bar, unsigned count)

@@ -35,13 +35,18 @@ CASES = [
     ("noise_s24_l8", 1024 * 2, 2, 24, 96000, "noise", 8, {"block_size": 1024}),
     ("wasted_l5", 1024, 2, 16, 44100, "wasted", 5, {"block_size": 1024}),
     ("silence_l8", 1024, 2, 16, 44100, "silence", 8, {"block_size": 1024}),
-    # the fused finish of k_search (16-bit, power-of-two blocks of 512..4096): partition order up to 8 (the level
+    # the fast finish of k_search (16-bit, power-of-two blocks of 512..4096): partition order up to 8 (the level
     # of single runs), one span only, Rice parameters above 14 (RICE2) and the variable-block-size splits
     ("fused_l9_vbs", 4096 + 100, 2, 16, 44100, "mix", 9, {}),
     ("fused_l10_bs512", 512 * 3, 2, 16, 44100, "mix", 10, {"block_size": 512, "variable_block_size": 0}),
     ("fused_l8_bs2048", 2048 * 2 + 17, 2, 16, 44100, "mix", 8, {"block_size": 2048}),
     ("fused_noise_l8", 4096, 2, 16, 44100, "noise", 8, {}),
     ("fused_noise_l10", 2048, 1, 16, 44100, "noise", 10, {"block_size": 2048, "variable_block_size": 0}),
+    # blocks of 8192: the order-32 kernel on 24-bit and on 16-bit input; 16-bit stereo frames of that size are four
+    # chunks through the two-stage TMA ring (a stage is refilled while fibers run ahead of the issuing one)
+    ("bs8192_l12_s24", 8192 + 300, 2, 24, 96000, "mix", 12, {"variable_block_size": 0}),
+    ("bs8192_l11_s16", 8192, 2, 16, 44100, "mix", 11, {}),
+    ("bs4096_l9_s24_8ch", 4096, 8, 24, 48000, "mix", 9, {"variable_block_size": 0}),
 ]
 
 

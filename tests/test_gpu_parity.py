@@ -28,6 +28,11 @@ CASES = [
     ("l10_s16",  4096 * 4, 2, 16, 44100, "impulses", 10, {}),
     ("l11_s24",  8192 * 3 + 2048, 2, 24, 96000, "mix", 11, {}),
     ("l12_s24",  8192 * 3 + 2048, 2, 24, 96000, "impulses", 12, {}),
+    # CD audio at the two highest presets: blocks of 8192 (four chunks through the two-stage TMA ring), the
+    # order-32 kernel on 16-bit input
+    ("l11_s16",  8192 * 3 + 1000, 2, 16, 44100, "mix", 11, {}),
+    ("l12_s16",  8192 * 2 + 4096, 2, 16, 44100, "impulses", 12, {}),
+    ("l8_bs8192_s16", 8192 * 3, 2, 16, 44100, "mix", 8, {"block_size": 8192}),
     ("l9_8ch",   4096 * 3 + 1024, 8, 24, 48000, "impulses", 9, {}),
     ("l8_mono",  4096 * 3 + 10, 1, 16, 44100, "mix", 8, {}),
     ("l8_noise", 4096 * 3, 2, 16, 44100, "noise", 8, {}),

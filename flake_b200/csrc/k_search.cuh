@@ -274,7 +274,7 @@ __device__ __noinline__ void fb_finish_warp(FbSearchShared<MAXP> &S, int slot, c
  * level is the smallest total, the finer one on a tie (rice.c:128-135): one minimum over
  * (bits, 31 - level, method).  Same posts as fb_finish_body.
  */
-#define FB_FAST_MAX_N 4096
+#define FB_FAST_MAX_N 8192
 
 __device__ __forceinline__ uint32_t fb_level_key(uint32_t x, int L)
 {
@@ -298,9 +298,13 @@ __device__ __noinline__ void fb_finish_fast(FbSearchShared<MAXP> &S, int slot, c
         for (int j = lane; j < (1 << L); j += 32) {
             const uint32_t *src = F32 + (j << e);
             uint32_t sum;
-            if (e == 3) {
-                const uint4 p = *reinterpret_cast<const uint4 *>(src), q = *reinterpret_cast<const uint4 *>(src + 4);
-                sum = ((p.x + p.y) + (p.z + p.w)) + ((q.x + q.y) + (q.z + q.w));
+            if (e >= 3) {                                         /* 8 run sums, 16 in blocks of 8192 */
+                sum = 0;
+#pragma unroll 1
+                for (int q4 = 0; q4 < (1 << e); q4 += 8) {
+                    const uint4 p = *reinterpret_cast<const uint4 *>(src + q4), q = *reinterpret_cast<const uint4 *>(src + q4 + 4);
+                    sum += ((p.x + p.y) + (p.z + p.w)) + ((q.x + q.y) + (q.z + q.w));
+                }
             } else if (e == 2) {
                 const uint4 p = *reinterpret_cast<const uint4 *>(src);
                 sum = (p.x + p.y) + (p.z + p.w);
@@ -352,6 +356,96 @@ __device__ __noinline__ void fb_finish_fast(FbSearchShared<MAXP> &S, int slot, c
         S.result[slot] = total;
         S.porder[slot] = none ? pmin : 31 - (int)((key >> 1) & 31u);
         S.method[slot] = (int)bmethod;
+    }
+}
+
+/*
+ * The same finish over 64-bit run sums, exact for any input (24-bit audio, whose residual bound
+ * cannot prove 32-bit partition sums; full-scale noise, where they really do not fit): the
+ * structure of fb_finish_fast -- vector loads, a partition per lane, one Rice computation for the
+ * five coarse levels -- with the always-exact arithmetic of fb_finish_body<unsigned long long>
+ * (costs truncated to uint32 as the reference computes them, rice.c:30-45; levels compared from
+ * the finest down, replaced only when strictly smaller).  n a power of two from 512 to FB_FAST_MAX_N.
+ */
+template <int MAXP>
+__device__ __noinline__ void fb_finish_fast64(FbSearchShared<MAXP> &S, int slot, const unsigned long long *F, int n,
+                                              int is_lpc, int order, int obits, int pmin, int pmax)
+{
+    const int lane = threadIdx.x & 31;
+    uint8_t *kbuf = S.kbuf[slot];
+    const int ltop = 27 - __clz(n);                               /* the level whose partitions are single runs */
+    uint32_t best = 0xffffffffu;
+    int bl = pmin, bmethod = 0;
+    unsigned long long a3 = 0;
+    const int lfirst = pmax < 5 ? 5 : (pmax < ltop ? pmax : ltop);
+#pragma unroll 1
+    for (int L = lfirst; L >= 5; L--) {
+        const int e = ltop - L;
+        uint32_t bits = 0;
+        int flag = 0;
+#pragma unroll 1
+        for (int j = lane; j < (1 << L); j += 32) {
+            const unsigned long long *src = F + (j << e);
+            unsigned long long sum = 0;
+            if (e == 0) sum = src[0];
+            else {
+#pragma unroll 1
+                for (int q = 0; q < (1 << e); q += 2) {
+                    const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(src + q);
+                    sum += p.x + p.y;
+                }
+            }
+            const int cnt = (16 << e) - (j == 0 ? order : 0);     /* runs of 16 samples (FB_RUN) */
+            const int k = fb_rice_k_t(sum, cnt);
+            kbuf[(1 << L) - 1 + j] = (uint8_t)k;
+            bits += fb_rice_count_t(sum, cnt, k);
+            flag |= (k > 14);
+            a3 = sum;                                             /* L == 5 comes last: the lane's own partition */
+        }
+        const uint32_t b = __reduce_add_sync(FB_FULL_MASK, bits) + 4u * (1u << L);
+        const int r2 = __any_sync(FB_FULL_MASK, flag) ? 1 : 0;
+        if (L <= pmax && L >= pmin && b < best) { best = b; bl = L; bmethod = r2; }
+    }
+    /* across the lanes: levels 4 .. 0, lane l costs partition l >> c of level 5 - c, c = 1 + ctz(l) */
+    if (pmin < 5) {
+        const unsigned long long c1 = a3 + __shfl_xor_sync(FB_FULL_MASK, a3, 1);
+        const unsigned long long c2 = c1 + __shfl_xor_sync(FB_FULL_MASK, c1, 2);
+        const unsigned long long c3 = c2 + __shfl_xor_sync(FB_FULL_MASK, c2, 4);
+        const unsigned long long c4 = c3 + __shfl_xor_sync(FB_FULL_MASK, c3, 8);
+        const unsigned long long c5 = c4 + __shfl_xor_sync(FB_FULL_MASK, c4, 16);
+        const int c = lane ? __ffs(lane) : 6;
+        const int Lc = 5 - c;
+        const unsigned long long sum = c == 1 ? c1 : (c == 2 ? c2 : (c == 3 ? c3 : (c == 4 ? c4 : c5)));
+        const int j = lane >> c;
+        const int cnt = (n >> (Lc < 0 ? 0 : Lc)) - (j == 0 ? order : 0);
+        const int k = fb_rice_k_t(sum, cnt);
+        const bool use = lane != 0 && Lc <= pmax && Lc >= pmin;
+        uint32_t x = use ? fb_rice_count_t(sum, cnt, k) : 0u;
+        if (use) kbuf[(1 << Lc) - 1 + j] = (uint8_t)k;
+        const uint32_t over = __ballot_sync(FB_FULL_MASK, use && k > 14);
+#pragma unroll
+        for (int o = 1; o < 5; o++) {
+            const uint32_t t = __shfl_xor_sync(FB_FULL_MASK, x, 1 << o);
+            if (o >= c) x += t;
+        }
+        /* lane 2^(c-1) holds the total of level 5 - c; the lanes of that role are those = 2^(c-1) mod 2^c */
+#pragma unroll
+        for (int cc = 1; cc <= 5; cc++) {
+            const int L = 5 - cc;
+            const uint32_t b = __shfl_sync(FB_FULL_MASK, x, 1 << (cc - 1)) + 4u * (1u << L);
+            const uint32_t role = cc == 1 ? 0xaaaaaaaau : (cc == 2 ? 0x44444444u : (cc == 3 ? 0x10101010u : (cc == 4 ? 0x01000100u : 0x00010000u)));
+            const int r2 = (over & role) ? 1 : 0;
+            if (L <= pmax && L >= pmin && b < best) { best = b; bl = L; bmethod = r2; }
+        }
+    }
+    if (lane == 0) {
+        uint32_t total = (uint32_t)(order * obits + 2);
+        if (is_lpc) total += 4u + 5u + (uint32_t)order * 15u;
+        total += best;
+        total += (uint32_t)bmethod + 4u;
+        S.result[slot] = total;
+        S.porder[slot] = bl;
+        S.method[slot] = bmethod;
     }
 }
 
@@ -893,6 +987,7 @@ __device__ __noinline__ void fb_eval_group(FbSearchShared<MAXP> &S, const FbSear
             const int order = fb_order_of(ord, s);
             const int pmin = S.pmin_of[order], pmax = S.pmax_of[order];
             if (rs32) fb_finish_fast<MAXP>(S, s, reinterpret_cast<const uint32_t *>(runsum0) + s * 2 * rstride, X.n, X.is_lpc, order, X.obits, pmin, pmax);
+            else if (X.fastable && !res_out) fb_finish_fast64<MAXP>(S, s, runsum0 + s * rstride, X.n, X.is_lpc, order, X.obits, pmin, pmax);
             else fb_finish_warp<MAXP>(S, s, runsum0 + s * rstride, (X.n >> pmax) / FB_RUN, X.n, X.is_lpc, order, X.obits, pmin, pmax);
         }
         FB_PROF(3);

@@ -38,6 +38,7 @@ struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 struct __attribute__((aligned(8))) int2 { int x, y; };
 struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+struct __attribute__((aligned(16))) ulonglong2 { unsigned long long x, y; };
 inline int4 make_int4(int x, int y, int z, int w) { int4 v = {x, y, z, w}; return v; }
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(FB_PREP_THREADS)
 k_vbs_split(FbConfig cfg, const void *pcm, int fmt, uint32_t nsamples,
             uint32_t *sizes, uint32_t *counts)
 {
-    __shared__ uint64_t red[32];
+    __shared__ uint64_t red[8 * 8];                              /* [warp][section], FB_PREP_THREADS <= 256 */
     __shared__ long long energy[8];
     const uint32_t B = (uint32_t)cfg.block_size;
     const uint32_t blk = blockIdx.x;
@@ -78,22 +78,38 @@ k_vbs_split(FbConfig cfg, const void *pcm, int fmt, uint32_t nsamples,
         return;
     }
     const uint32_t sec = n / 8;
+    /* Sum over channels and j = 2..sec-1 of |x[j] - 2 x[j-1] + x[j-2]| (int32 wrap + abs(int), vbs.c:52-60).
+     * A thread owns a channel and a range of consecutive j, so that x[j-1] and x[j-2] stay in registers
+     * (one load per element instead of three; a 24-bit sample is three byte loads); the threads of a
+     * channel group read neighbouring channels of the same sample.  Unsigned 64-bit adds in any order. */
+    const int G = (int)blockDim.x / C;                           /* ranges per section (blockDim >= 8 channels) */
+    const int c = (int)threadIdx.x % C, g = (int)threadIdx.x / C;
+    const uint32_t len = (sec - 2u + (uint32_t)G - 1u) / (uint32_t)G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = ((int)blockDim.x + 31) >> 5;
     for (int s = 0; s < 8; s++) {
-        /* sum over channels and j = 2..sec-1 of |x[j] - 2x[j-1] + x[j-2]|, int32 wrap + abs(int) */
-        const size_t base = ((size_t)start + (size_t)s * sec) * (size_t)C;
-        const uint32_t items = (sec - 2) * (uint32_t)C;
         uint64_t acc = 0;
-        for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
-            const size_t idx = base + 2u * (uint32_t)C + it;      /* element (j, ch) with j >= 2 */
-            uint32_t x0 = (uint32_t)fb_load_pcm(pcm, fmt, idx);
-            uint32_t x1 = (uint32_t)fb_load_pcm(pcm, fmt, idx - (size_t)C);
-            uint32_t x2 = (uint32_t)fb_load_pcm(pcm, fmt, idx - 2 * (size_t)C);
-            int32_t v = (int32_t)(x0 - 2u * x1 + x2);
-            int32_t a = v < 0 ? (int32_t)(0u - (uint32_t)v) : v;
-            acc += (uint64_t)(int64_t)a;
+        const uint32_t j0 = 2u + (uint32_t)g * len, j1 = min(sec, j0 + len);
+        if (g < G && j0 < j1) {
+            const size_t e0 = ((size_t)start + (size_t)s * sec) * (size_t)C + (size_t)c;   /* element (0, c) of the section */
+            uint32_t x2 = (uint32_t)fb_load_pcm(pcm, fmt, e0 + (size_t)(j0 - 2u) * (size_t)C);
+            uint32_t x1 = (uint32_t)fb_load_pcm(pcm, fmt, e0 + (size_t)(j0 - 1u) * (size_t)C);
+#pragma unroll 4
+            for (uint32_t j = j0; j < j1; j++) {
+                const uint32_t x0 = (uint32_t)fb_load_pcm(pcm, fmt, e0 + (size_t)j * (size_t)C);
+                const int32_t v = (int32_t)(x0 - 2u * x1 + x2);
+                const int32_t a = v < 0 ? (int32_t)(0u - (uint32_t)v) : v;
+                acc += (uint64_t)(int64_t)a;
+                x2 = x1; x1 = x0;
+            }
         }
-        acc = fb_block_sum_u64(acc, red);
-        if (threadIdx.x == 0) energy[s] = (long long)acc / C + 1;
+        acc = fb_warp_sum_u64(acc);
+        if (lane == 0) red[warp * 8 + s] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        uint64_t acc = 0;
+        for (int w = 0; w < nw; w++) acc += red[w * 8 + (int)threadIdx.x];
+        energy[threadIdx.x] = (long long)acc / C + 1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {

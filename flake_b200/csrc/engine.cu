@@ -424,7 +424,8 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     FB_MARK(4);
     /* threads per frame by the work in it (measured: 8192 samples per frame 1.75 ms with 128 threads vs
      * 1.88 with 256 per C2 stream; 32768 samples per frame 2.79 vs 2.08) */
-    const int pack_threads = (uint64_t)B * (uint64_t)cfg.channels >= 16384u ? FB_PACK_THREADS : FB_PACK_THREADS / 2;
+    /* a pass of a few blocks (flake_encode_frame: one) is a latency chain: shorter runs per thread */
+    const int pack_threads = ((uint64_t)B * (uint64_t)cfg.channels >= 16384u || nblocks <= 32u) ? FB_PACK_THREADS : FB_PACK_THREADS / 2;
     FB_LAUNCH(k_pack, dim3(grid_frames), dim3(pack_threads), (size_t)e->pack_smem_words * 4, st,
               cfg, e->d_frames, e->d_nframes, d_pcm, fmt, e->d_smp, e->d_res, e->d_subs, e->d_modes, e->d_slots,
               flen, d_frame_bs, e->pack_smem_words, e->d_xpow32, e->d_crc16tab,

@@ -511,27 +511,30 @@ k_lpc_lat(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const vo
      * loads and products of a batch are independent, only the additions form the chain */
     int j = lag + 1 + ca;
     const int jend = n - 1 + ca;                           /* last position, inclusive */
+    /* dl[s][j] = data1[j - lag of the chain]; a lane without a chain walks lag 0 and its sums are never
+     * read: no select per product, the loads are base + constant */
+    const double *dl[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) dl[s] = d - (lagi[s] >= 0 ? lagi[s] : 0);
     for (; j + 14 <= jend; j += 16) {
         double pr[NS][8];
+        const double *dj = d + j;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const double dj = d[j + 2 * u];
+            const double x = dj[2 * u];
 #pragma unroll
-            for (int s = 0; s < NS; s++)
-                pr[s][u] = lagi[s] >= 0 ? __dmul_rn(dj, d[j + 2 * u - lagi[s]]) : 0.0;
+            for (int s = 0; s < NS; s++) pr[s][u] = __dmul_rn(x, dl[s][j + 2 * u]);
         }
 #pragma unroll
-        for (int s = 0; s < NS; s++)
-            if (lagi[s] >= 0) {
+        for (int s = 0; s < NS; s++) {
 #pragma unroll
-                for (int u = 0; u < 8; u++) acc[s] = __dadd_rn(acc[s], pr[s][u]);
-            }
+            for (int u = 0; u < 8; u++) acc[s] = __dadd_rn(acc[s], pr[s][u]);
+        }
     }
     for (; j <= jend; j += 2) {
-        const double dj = d[j];
+        const double x = d[j];
 #pragma unroll
-        for (int s = 0; s < NS; s++)
-            if (lagi[s] >= 0) acc[s] = __dadd_rn(acc[s], __dmul_rn(dj, d[j - lagi[s]]));
+        for (int s = 0; s < NS; s++) acc[s] = __dadd_rn(acc[s], __dmul_rn(x, dl[s][j]));
     }
 
     /* autoc[i] = temp + temp2 (lpc.c:67), gathered to every lane */

@@ -331,9 +331,13 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
     }
 #define FB_STEP(call_, what_) do { if (fb_step_failed(e, st, (call_), (what_))) return -4; } while (0)
 #define FB_LAUNCHED(what_) FB_STEP(cudaSuccess, what_)
-    FB_STEP(cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st), "clearing the frame count");   /* frame count, -, pack ticket, - */
-    FB_STEP(cudaMemsetAsync(e->d_status, 0, sizeof(unsigned long long) * (size_t)grid_frames, st), "clearing the look-back status");
-    FB_STEP(cudaMemsetAsync(d_summary, 0, sizeof(FbSummary), st), "clearing the chunk summary");
+    /* frame count, -, pack ticket, -; look-back status; chunk summary.  With fixed blocks k_frames_fixed
+     * clears them itself (three launches less per pass: 7 us of a one-block flake_encode_frame call) */
+    if (cfg.variable_block_size) {
+        FB_STEP(cudaMemsetAsync(e->d_nframes, 0, sizeof(uint32_t) * 4, st), "clearing the frame count");
+        FB_STEP(cudaMemsetAsync(e->d_status, 0, sizeof(unsigned long long) * (size_t)grid_frames, st), "clearing the look-back status");
+        FB_STEP(cudaMemsetAsync(d_summary, 0, sizeof(FbSummary), st), "clearing the chunk summary");
+    }
     FB_MARK(0);
     if (cfg.variable_block_size) {
         FB_LAUNCH(k_vbs_split, dim3(nblocks), dim3(FB_PREP_THREADS), 0, st,
@@ -345,7 +349,7 @@ extern "C" int fb_engine_encode_device(FbEngine *e, const void *d_pcm, int fmt, 
         e->launches += 2;
     } else {
         FB_LAUNCH(k_frames_fixed, dim3((nblocks + 255) / 256), dim3(256), 0, st,
-                  cfg, ns, first_number, e->d_frames, e->d_nframes);
+                  cfg, ns, first_number, e->d_frames, e->d_nframes, e->d_status, (FbSummary *)d_summary);
         FB_LAUNCHED("k_frames_fixed");
         e->launches += 1;
     }

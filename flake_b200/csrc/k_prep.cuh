@@ -35,8 +35,10 @@ __host__ __device__ __forceinline__ uint32_t fb_slot_offset(uint32_t frame_index
 }
 
 /* fixed block size: frame f = block f (encode.c:979-1005 without VBS) */
+/* Also clears what k_pack counts in: its ticket (nframes[2]), the look-back status of every frame and
+ * the chunk summary. */
 __global__ void k_frames_fixed(FbConfig cfg, uint32_t nsamples, uint32_t first_number,
-                               FbFrame *frames, uint32_t *nframes)
+                               FbFrame *frames, uint32_t *nframes, unsigned long long *status, FbSummary *summary)
 {
     const uint32_t B = (uint32_t)cfg.block_size;
     const uint32_t nf = (nsamples + B - 1) / B;
@@ -47,8 +49,13 @@ __global__ void k_frames_fixed(FbConfig cfg, uint32_t nsamples, uint32_t first_n
         fr.number = first_number + (cfg.allow_vbs ? fr.start : f);
         fr.slot = fb_slot_offset(f, fr.start, cfg.channels, cfg.bps);
         frames[f] = fr;
+        status[f] = 0ull;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *nframes = nf;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        nframes[0] = nf; nframes[1] = 0; nframes[2] = 0; nframes[3] = 0;
+        summary->nframes = 0; summary->max_frame_bytes = 0; summary->total_bytes = 0;
+        summary->verbatim_frames = 0; summary->min_frame_inv = 0;
+    }
 }
 
 /*

@@ -1313,29 +1313,27 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
     } else {
         /* log search, optimize.c:241-261.  A step's candidates are last-step, last, last+step; which
          * orders are costed next depends only on the decisions so far, so the decision tree comes
-         * tabulated from the host (FbPlanNode, engine.h): cost the node's group, replay its steps on
-         * the totals exactly as the reference runs them, follow the child of the winner. */
-        uint32_t done = 0;
-        const int lo = min_order - 1, hi = max_order - 1;
+         * tabulated from the host (FbPlanNode, engine.h): cost the node's group, take the first
+         * strict minimum over its members IN THEIR ORDER, follow the child of the winner.  That is
+         * the reference's replay: the planner merges steps into a node only while the new
+         * candidates of every step are the same whichever order is the best by then, and lists
+         * them step by step, ascending inside a step -- the sequence in which optimize.c:249-258
+         * compares them with `<` (the walk over steps and neighbours that used to stand here, with
+         * its done-mask and its search for each candidate's slot, was 8 % of a CTA's life). */
         uint32_t node = 0;
         opt_order = (int)plan[0].start_order;
-        int step = 16;
         while (node != FB_PLAN_END) {
             const FbPlanNode nd = node < FB_PLAN_SMEM_NODES ? S.plan[node] : plan[node];
-            const int cnt = (int)nd.cnt, nsteps = (int)nd.nsteps;
+            const int cnt = (int)nd.cnt;
             ord = nd.ord;
             FB_PROF(5);
             fb_eval_group<MAXP>(S, X, cnt, ord, nullptr FB_PROF_PASS);
             int bs = -1;
-            for (int k = 0; k < nsteps; k++, step >>= 1) {
-                const int last = opt_order;
-                for (int i = last - step; i <= last + step; i += step) {
-                    if (i < lo || i > hi || ((done >> i) & 1u)) continue;
-                    int s = 0;
-                    for (int q = 1; q < FB_GROUP_OF(MAXP); q++) if (q < cnt && fb_order_of(ord, q) == i + 1) s = q;
+#pragma unroll
+            for (int s = 0; s < FB_GROUP_OF(MAXP); s++) {
+                if (s < cnt) {
                     const uint32_t b = S.result[s];
-                    done |= 1u << i;
-                    if (b < best) { best = b; opt_order = i; bs = s; }
+                    if (b < best) { best = b; opt_order = fb_order_of(ord, s) - 1; bs = s; }
                 }
             }
             if (bs >= 0) fb_keep_best<MAXP>(S, bs, best);

@@ -125,13 +125,17 @@ __device__ __forceinline__ void fb_levinson_update(double (&a)[ML], int i, doubl
     if (i & 1) a[half] = __dadd_rn(a[half], __dmul_rn(a[half], r));
 }
 
+/* A row's shift (0 .. 15) travels with the sum of its |coefficients| (< 2^19, bits 8 and up): k_search
+ * needs both for its 32-bit exactness tests and would otherwise add up every row of every subframe behind
+ * a barrier of its own. */
 template <int ML>
 __device__ __forceinline__ void fb_store_row(int32_t *co, int32_t *so, int rowi, const int32_t (&q)[ML], int32_t sh)
 {
+    uint32_t sa = 0;
 #pragma unroll
     for (int j = 0; j < ML; j++)
-        if (j <= rowi) co[rowi * FB_MAX_ORDER + j] = q[j];
-    so[rowi] = sh;
+        if (j <= rowi) { co[rowi * FB_MAX_ORDER + j] = q[j]; sa += (uint32_t)(q[j] < 0 ? -q[j] : q[j]); }
+    so[rowi] = (int32_t)((uint32_t)sh | (sa << 8));
 }
 
 /*
@@ -190,10 +194,7 @@ __device__ __forceinline__ void fb_lpc_rows(const FbConfig &cfg, const double (&
         for (int j = 0; j < ML; j++) rowv[j] = -a[j];
         fb_quantize<ML>(rowv, est, q, sh);
         if (writer) {
-#pragma unroll
-            for (int j = 0; j < ML; j++)
-                if (j < est) co[(est - 1) * FB_MAX_ORDER + j] = q[j];
-            so[est - 1] = sh;
+            fb_store_row<ML>(co, so, est - 1, q, sh);
             sb->est_order = est;
         }
         return;

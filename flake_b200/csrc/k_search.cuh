@@ -1143,7 +1143,19 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
             const int rowi = e / MAXP, j = e % MAXP;
             S.coef[rowi][j] = (rowi < max_order && j <= rowi) ? co[rowi * FB_MAX_ORDER + j] : 0;
         }
-        for (int rowi = tid; rowi < MAXP; rowi += T) S.shift[rowi] = rowi < max_order ? so[rowi] : 0;
+        /* shift | sum |c| << 8 per row (k_lpc, fb_store_row); the 32-bit exactness tests right here, in front of
+         * the staging barrier */
+        for (int rowi = tid; rowi < MAXP; rowi += T) {
+            const uint32_t v = rowi < max_order ? (uint32_t)so[rowi] : 0u;
+            const int sh = (int)(v & 0xffu);
+            const uint32_t sa = v >> 8;                                 /* <= 32 * 16383 */
+            S.shift[rowi] = sh;
+            S.sumabs[rowi] = sa;
+            const unsigned long long pm = (unsigned long long)sa * (unsigned long long)sb_maxabs;
+            const unsigned long long rb = (unsigned long long)sb_maxabs + (pm >> sh) + 1ull;   /* bound on |residual| */
+            S.narrow_of[rowi] = pm < 0x80000000ull && rb < (1ull << 26);
+            S.sum32_of[rowi] = 2ull * rb * (unsigned long long)n < 0x80000000ull;   /* zig-zag <= 2 rb: every partition sum < 2^31 */
+        }
     }
     if (cfg.order_method == 6 && tid < (int)(FB_PLAN_SMEM_NODES * sizeof(FbPlanNode) / 4))   /* engine.cu pads the plan */
         reinterpret_cast<uint32_t *>(S.plan)[tid] = reinterpret_cast<const uint32_t *>(plan)[tid];
@@ -1211,25 +1223,12 @@ k_search(FbConfig cfg, const FbFrame *frames, const uint32_t *nframes, const voi
     }
 
     __syncthreads();
-    if (!fixed) {
-        /* sum |c| per row from the staged rows (a loop of dependent global loads here cost more
-         * than the rest of the staging) */
-        for (int rowi = tid; rowi < MAXP; rowi += T) {
-            uint32_t sa = 0;
-#pragma unroll
-            for (int j = 0; j < MAXP; j++) { const int32_t v = S.coef[rowi][j]; sa += (uint32_t)(v < 0 ? -v : v); }
-            S.sumabs[rowi] = sa;                                    /* <= 32 * 16383 */
-            const unsigned long long pm = (unsigned long long)sa * (unsigned long long)sb_maxabs;
-            const unsigned long long rb = (unsigned long long)sb_maxabs + (pm >> S.shift[rowi]) + 1ull;   /* bound on |residual| */
-            S.narrow_of[rowi] = pm < 0x80000000ull && rb < (1ull << 26);
-            S.sum32_of[rowi] = 2ull * rb * (unsigned long long)n < 0x80000000ull;   /* zig-zag <= 2 rb: every partition sum < 2^31 */
-        }
+    if (!fixed && FB_F64_WIDE(MAXP)) {
         /* the rows for the FP64 bodies: coefficient * 2^-shift, exact */
-        if (FB_F64_WIDE(MAXP))
-            for (int e = tid; e < MAXP * MAXP; e += T) {
-                const int rowi = e / MAXP, j = e % MAXP;
-                S.coefd[rowi][j] = (double)S.coef[rowi][j] * fb_exp2_neg(S.shift[rowi]);
-            }
+        for (int e = tid; e < MAXP * MAXP; e += T) {
+            const int rowi = e / MAXP, j = e % MAXP;
+            S.coefd[rowi][j] = (double)S.coef[rowi][j] * fb_exp2_neg(S.shift[rowi]);
+        }
         __syncthreads();
     }
     FB_PROF(0);
